@@ -1,0 +1,335 @@
+// Batched Cholesky (A = L L^T), the reference's `int top(matrix_t A[N][N], matrix_t L[N][N])`
+// (Cholesky/cholesky_v*/model4x4/chol.h:15-16) over a batch of row-major matrices.
+//
+// Two arithmetic variants, each bit-identical to the reference designs it replaces:
+//   variant 0  right-looking: cholesky_v1.3 (chol.cpp:25-63), v3.2 (chol.cpp:94-181), v4.0 (chol.cpp:64-130)
+//   variant 1  "revised" root-free elimination + final scaling: cholesky_v2.2 (chol.cpp:28-207)
+//
+// Kernels:
+//   chol_tpm_kernel<N>   thread-per-matrix, N in {4, 8, 16}: each warp owns a shared-memory slab of
+//                        32 padded matrix slots filled by 1-D bulk async copies (TMA engine), each
+//                        thread factors its matrix entirely in registers and the slab is written
+//                        back with bulk stores.  HBM-bound (2*N*N*4 bytes per matrix).
+//   chol_group_kernel<G> G threads per matrix, matrix resident in shared memory: any N that fits.
+//   chol_global_kernel   one CTA per matrix, working in place in global memory/L2: any N (slow, exact).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace hlsd {
+
+// ------------------------------------------------------------------------------------------------
+// thread-per-matrix
+// ------------------------------------------------------------------------------------------------
+template <int N>
+struct TpmCfg {
+    static constexpr int kSlot = N * N + 4;  // floats; +16 B so that 8 consecutive slots hit 8 bank groups
+    static constexpr int kSlabFloats = 32 * kSlot;
+    static constexpr int kMatBytes = N * N * 4;
+};
+
+template <int N, int VARIANT>
+__device__ __forceinline__ void chol_regs(float (&a)[N * (N + 1) / 2]) {
+#define T(i, j) ((i) * ((i) + 1) / 2 + (j))
+    if constexpr (VARIANT == 0) {
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            float d = xsqrt(a[T(k, k)]);
+            a[T(k, k)] = d;
+#pragma unroll
+            for (int i = k + 1; i < N; i++) a[T(i, k)] = xdiv(a[T(i, k)], d);
+#pragma unroll
+            for (int i = k + 1; i < N; i++)
+#pragma unroll
+                for (int j = i; j < N; j++) a[T(j, i)] = xmsub(a[T(j, i)], a[T(j, k)], a[T(i, k)]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            float d = a[T(k, k)];
+            float m[N];
+#pragma unroll
+            for (int i = k + 1; i < N; i++) m[i] = xdiv(a[T(i, k)], d);
+#pragma unroll
+            for (int i = k + 1; i < N; i++)
+#pragma unroll
+                for (int j = i; j < N; j++) a[T(j, i)] = xmsub(a[T(j, i)], a[T(j, k)], m[i]);
+#pragma unroll
+            for (int i = k + 1; i < N; i++) a[T(i, k)] = m[i];
+        }
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            float r = xsqrt(a[T(k, k)]);
+            a[T(k, k)] = r;
+#pragma unroll
+            for (int j = k + 1; j < N; j++) a[T(j, k)] = xmul(a[T(j, k)], r);
+        }
+    }
+#undef T
+}
+
+template <int N, int VARIANT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+chol_tpm_kernel(const float* __restrict__ A, float* __restrict__ L, long batch) {
+    using Cfg = TpmCfg<N>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* slabs = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * Cfg::kSlabFloats * 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* slab = slabs + (size_t)warp * Cfg::kSlabFloats;
+    float* slot = slab + lane * Cfg::kSlot;
+    uint64_t* bar = bars + warp;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+
+    const long num_slabs = (batch + 31) / 32;
+    uint32_t parity = 0;
+    for (long s = (long)blockIdx.x * WARPS + warp; s < num_slabs; s += (long)gridDim.x * WARPS) {
+        const long m0 = s * 32;
+        const int valid = (int)min(32L, batch - m0);
+        // the bulk store that last read this slot (issued by this very thread) must have drained
+        bulk_wait_read<0>();
+        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * Cfg::kMatBytes);
+        __syncwarp();
+        if (lane < valid) bulk_g2s(slot, A + (m0 + lane) * (long)(N * N), Cfg::kMatBytes, bar);
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        if (lane < valid) {
+            float a[N * (N + 1) / 2];
+            const float4* s4 = reinterpret_cast<const float4*>(slot);
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int q = 0; q <= i / 4; q++) {
+                    float4 v = s4[i * (N / 4) + q];
+                    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+                        if (4 * q + t <= i) a[i * (i + 1) / 2 + 4 * q + t] = e[t];
+                }
+            chol_regs<N, VARIANT>(a);
+            float4* d4 = reinterpret_cast<float4*>(slot);
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int q = 0; q < N / 4; q++) {
+                    float e[4];
+#pragma unroll
+                    for (int t = 0; t < 4; t++) e[t] = (4 * q + t <= i) ? a[i * (i + 1) / 2 + 4 * q + t] : 0.0f;
+                    d4[i * (N / 4) + q] = make_float4(e[0], e[1], e[2], e[3]);
+                }
+            fence_async_smem();
+            bulk_s2g(L + (m0 + lane) * (long)(N * N), slot, Cfg::kMatBytes);
+            bulk_commit();
+        }
+    }
+    bulk_wait_read<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// G threads per matrix, matrix resident in shared memory
+// ------------------------------------------------------------------------------------------------
+template <int G, int VARIANT>
+__global__ void __launch_bounds__(256)
+chol_group_kernel(const float* __restrict__ A, float* __restrict__ L, int n, long batch) {
+    extern __shared__ __align__(16) float smem_f[];
+    constexpr int kGroups = 256 / G;
+    const int g = threadIdx.x / G, t = threadIdx.x % G;
+    const int ld = n | 1;  // odd leading dimension: column walks do not collide on one bank
+    float* w = smem_f + (size_t)g * ((size_t)n * ld + n);
+    float* mcol = w + (size_t)n * ld;  // variant 1: multipliers of the current stage
+    const long nn = (long)n * n;
+    for (long b = (long)blockIdx.x * kGroups + g; b < batch; b += (long)gridDim.x * kGroups) {
+        const float* a = A + b * nn;
+        for (int e = t; e < n * n; e += G) {
+            int i = e / n, j = e - i * n;
+            w[i * ld + j] = a[e];
+        }
+        group_sync<G>(g);
+        for (int k = 0; k < n; k++) {
+            if constexpr (VARIANT == 0) {
+                float d = xsqrt(w[k * ld + k]);
+                group_sync<G>(g);  // everyone has read the un-rooted pivot
+                if (t == 0) w[k * ld + k] = d;
+                for (int i = k + 1 + t; i < n; i += G) w[i * ld + k] = xdiv(w[i * ld + k], d);
+                group_sync<G>(g);
+                // a[j][i] -= l[j][k] * l[i][k], k < i <= j  (flattened over the (j, i) rectangle)
+                const int m = n - k - 1;
+                for (int e = t; e < m * m; e += G) {
+                    int jj = e / m, ii = e - jj * m;
+                    if (ii <= jj) {
+                        int j = k + 1 + jj, i = k + 1 + ii;
+                        w[j * ld + i] = xmsub(w[j * ld + i], w[j * ld + k], w[i * ld + k]);
+                    }
+                }
+                group_sync<G>(g);
+            } else {
+                float d = w[k * ld + k];
+                for (int i = k + 1 + t; i < n; i += G) mcol[i] = xdiv(w[i * ld + k], d);
+                group_sync<G>(g);
+                const int m = n - k - 1;
+                for (int e = t; e < m * m; e += G) {
+                    int jj = e / m, ii = e - jj * m;
+                    if (ii <= jj) {
+                        int j = k + 1 + jj, i = k + 1 + ii;
+                        w[j * ld + i] = xmsub(w[j * ld + i], w[j * ld + k], mcol[i]);
+                    }
+                }
+                group_sync<G>(g);
+                for (int i = k + 1 + t; i < n; i += G) w[i * ld + k] = mcol[i];
+                group_sync<G>(g);
+            }
+        }
+        if constexpr (VARIANT == 1) {
+            for (int k = t; k < n; k += G) mcol[k] = xsqrt(w[k * ld + k]);
+            group_sync<G>(g);
+        }
+        float* l = L + b * nn;
+        for (int e = t; e < n * n; e += G) {
+            int i = e / n, j = e - i * n;
+            float v = 0.0f;
+            if (j <= i) {
+                v = w[i * ld + j];
+                if constexpr (VARIANT == 1) v = (i == j) ? mcol[j] : xmul(v, mcol[j]);
+            }
+            l[e] = v;
+        }
+        group_sync<G>(g);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one CTA per matrix, in place in global memory (any N; exact; slow)
+// ------------------------------------------------------------------------------------------------
+template <int VARIANT>
+__global__ void __launch_bounds__(1024)
+chol_global_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restrict__ scratch, int n, long batch) {
+    const int t = threadIdx.x, G = blockDim.x;
+    const long nn = (long)n * n;
+    for (long b = blockIdx.x; b < batch; b += gridDim.x) {
+        const float* a = A + b * nn;
+        float* w = L + b * nn;
+        float* mcol = scratch + (long)blockIdx.x * n;
+        for (long e = t; e < nn; e += G) w[e] = a[e];
+        __syncthreads();
+        for (int k = 0; k < n; k++) {
+            const int m = n - k - 1;
+            if constexpr (VARIANT == 0) {
+                float d = xsqrt(w[(long)k * n + k]);
+                __syncthreads();
+                if (t == 0) w[(long)k * n + k] = d;
+                for (int i = k + 1 + t; i < n; i += G) w[(long)i * n + k] = xdiv(w[(long)i * n + k], d);
+                __syncthreads();
+                for (long e = t; e < (long)m * m; e += G) {
+                    int jj = (int)(e / m), ii = (int)(e - (long)jj * m);
+                    if (ii <= jj) {
+                        long j = k + 1 + jj, i = k + 1 + ii;
+                        w[j * n + i] = xmsub(w[j * n + i], w[j * n + k], w[i * n + k]);
+                    }
+                }
+                __syncthreads();
+            } else {
+                float d = w[(long)k * n + k];
+                for (int i = k + 1 + t; i < n; i += G) mcol[i] = xdiv(w[(long)i * n + k], d);
+                __syncthreads();
+                for (long e = t; e < (long)m * m; e += G) {
+                    int jj = (int)(e / m), ii = (int)(e - (long)jj * m);
+                    if (ii <= jj) {
+                        long j = k + 1 + jj, i = k + 1 + ii;
+                        w[j * n + i] = xmsub(w[j * n + i], w[j * n + k], mcol[i]);
+                    }
+                }
+                __syncthreads();
+                for (int i = k + 1 + t; i < n; i += G) w[(long)i * n + k] = mcol[i];
+                __syncthreads();
+            }
+        }
+        if constexpr (VARIANT == 1) {
+            for (int k = t; k < n; k += G) mcol[k] = xsqrt(w[(long)k * n + k]);
+            __syncthreads();
+        }
+        for (long e = t; e < nn; e += G) {
+            int i = (int)(e / n), j = (int)(e - (long)i * n);
+            float v = 0.0f;
+            if (j <= i) {
+                v = w[e];
+                if constexpr (VARIANT == 1) v = (i == j) ? mcol[j] : xmul(v, mcol[j]);
+            }
+            w[e] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side dispatch
+// ------------------------------------------------------------------------------------------------
+template <int N, int VARIANT>
+static cudaError_t launch_tpm(const float* A, float* L, long batch, cudaStream_t st) {
+    constexpr int WARPS = (N == 16) ? 6 : 8;
+    using Cfg = TpmCfg<N>;
+    const size_t smem = (size_t)WARPS * Cfg::kSlabFloats * 4 + WARPS * sizeof(uint64_t);
+    auto kern = chol_tpm_kernel<N, VARIANT, WARPS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long num_slabs = (batch + 31) / 32;
+    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024) / (smem + 1024)));
+    long grid = std::min<long>((num_slabs + WARPS - 1) / WARPS, (long)sm_count() * ctas_per_sm);
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(A, L, batch);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int G, int VARIANT>
+static cudaError_t launch_group(const float* A, float* L, int n, long batch, cudaStream_t st) {
+    constexpr int kGroups = 256 / G;
+    const size_t per = ((size_t)n * (n | 1) + n) * 4;
+    const size_t smem = per * kGroups;
+    auto kern = chol_group_kernel<G, VARIANT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(227 * 1024) / (smem + 1024)));
+    long grid = std::min<long>((batch + kGroups - 1) / kGroups, (long)sm_count() * ctas_per_sm);
+    kern<<<(unsigned)grid, 256, smem, st>>>(A, L, n, batch);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int VARIANT>
+static cudaError_t chol_dispatch(const float* A, float* L, int n, long batch, int path, cudaStream_t st) {
+    const bool aligned = (((uintptr_t)A | (uintptr_t)L) & 15) == 0;
+    if (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM) {
+        if (aligned && n == 4) return launch_tpm<4, VARIANT>(A, L, batch, st);
+        if (aligned && n == 8) return launch_tpm<8, VARIANT>(A, L, batch, st);
+        if (aligned && n == 16) return launch_tpm<16, VARIANT>(A, L, batch, st);
+        if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
+    }
+    const size_t per = ((size_t)n * (n | 1) + n) * 4;
+    const size_t cap = 227 * 1024 - 1024;
+    if ((path == HLSD_PATH_AUTO && per <= cap) || path == HLSD_PATH_GROUP) {
+        if (per > cap) return cudaErrorInvalidValue;
+        if (n <= 48 && per * 8 <= cap) return launch_group<32, VARIANT>(A, L, n, batch, st);
+        if (n <= 96 && per * 2 <= cap) return launch_group<128, VARIANT>(A, L, n, batch, st);
+        return launch_group<256, VARIANT>(A, L, n, batch, st);
+    }
+    // global-memory fallback
+    float* scratch = nullptr;
+    long grid = std::min<long>(batch, (long)sm_count() * 2);
+    cudaError_t e = cudaMallocAsync(&scratch, sizeof(float) * (size_t)grid * n, st);
+    if (e != cudaSuccess) return e;
+    chol_global_kernel<VARIANT><<<(unsigned)grid, 1024, 0, st>>>(A, L, scratch, n, batch);
+    count_launch();
+    e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    return e;
+}
+
+cudaError_t cholesky_exact(const float* A, float* L, int n, long batch, int variant, int path, cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    return variant == 1 ? chol_dispatch<1>(A, L, n, batch, path, st) : chol_dispatch<0>(A, L, n, batch, path, st);
+}
+
+}  // namespace hlsd

@@ -1,0 +1,92 @@
+// Shared device/host helpers for the batched decomposition kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hlsd {
+
+// ----------------------------------------------------------------------------------------------
+// Exact arithmetic.  The reference's C-simulation rounds every float operation separately
+// (g++ on baseline x86-64: no FMA; e.g. `mid_L[j][i] - mid_L[j][id] * mid_L[i][id]`,
+// Cholesky/cholesky_v1.3/model4x4/chol.cpp:59).  The intrinsics below are never contracted by
+// nvcc into FFMA and use IEEE division / square root, so a kernel that performs the reference's
+// operations in the reference's per-element order reproduces its results bit for bit.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float xsqrt(float a) { return __fsqrt_rn(a); }
+// a - b*c, two roundings
+__device__ __forceinline__ float xmsub(float a, float b, float c) { return __fsub_rn(a, __fmul_rn(b, c)); }
+
+// qrf_mm of the reference (QR/qr_v2.1/model4x4/qr.cpp:52-60): a' = op2*s + op1*c ; b' = op2*c - op1*s
+__device__ __forceinline__ void givens_apply(float c, float s, float& op1, float& op2) {
+    float a = xadd(xmul(op2, s), xmul(op1, c));
+    float b = xsub(xmul(op2, c), xmul(op1, s));
+    op1 = a;
+    op2 = b;
+}
+
+// ----------------------------------------------------------------------------------------------
+// mbarrier + 1-D bulk async copies (TMA engine, SASS: UBLKCP).  Sizes and both addresses must be
+// multiples of 16 bytes.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared::cta, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared::cta -> global, tracked by the per-thread bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the bulk stores of all but the newest `N` groups have finished READING shared memory
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// make generic-proxy writes to shared memory visible to the async proxy (before bulk_s2g)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Group of G threads (G a power of two, 32 <= G <= 1024, groups aligned inside the CTA) that
+// works on one matrix.  A warp-sized group synchronises with __syncwarp, larger ones with a
+// named barrier (ids 1..15; id 0 is __syncthreads).
+template <int G>
+__device__ __forceinline__ void group_sync(int group_in_cta) {
+    if constexpr (G == 32) __syncwarp();
+    else named_bar_sync(1 + group_in_cta, G);
+}
+
+}  // namespace hlsd

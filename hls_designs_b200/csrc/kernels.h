@@ -1,0 +1,26 @@
+// Internal interface between the C-ABI layer (cabi.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include "../../include/hlsd.h"
+
+namespace hlsd {
+
+void count_launch();  // bumps the process-wide launch counter reported by hlsd_launch_count()
+int sm_count();
+
+// Exact paths: every float operation of the reference design, in its per-element order, rounded
+// separately.  `path` is one of HLSD_PATH_* (AUTO picks by size).  All enqueue on `st`.
+cudaError_t cholesky_exact(const float* A, float* L, int n, long batch, int variant, int path, cudaStream_t st);
+cudaError_t lu_exact(const float* A, float* L, float* U, int* P, int n, long batch, int pivoting, int path,
+                     cudaStream_t st);
+cudaError_t qr_exact(const float* A, float* Q, float* R, int rows, int cols, long batch, int variant, int path,
+                     cudaStream_t st);
+
+// Blocked right-looking Cholesky for large N (n % 64 == 0, n >= 128): SIMT panel factorisation +
+// trailing update on CUDA cores in the reference's per-element order (use_tensor == 0, exact) or
+// on the tcgen05 tensor cores (use_tensor == 1).  cudaErrorNotSupported when the size is not served.
+cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int use_tensor, cudaStream_t st);
+
+}  // namespace hlsd

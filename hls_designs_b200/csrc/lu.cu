@@ -1,0 +1,300 @@
+// Batched LU, the reference's `int top(A, L, U, P)` (LU/lu_v*/model4x4/lu.h:19-22): Doolittle
+// elimination with partial pivoting, LINPACK-style row exchanges (rows k and P[k] are exchanged in
+// columns >= k only; L columns already produced are not touched), lu_v1.1/model4x4/lu.cpp:23-92.
+// lu_v1.2 and lu_v2.1 reorder the same per-element operations (checked bit for bit in the CPU
+// tests), so one arithmetic serves the three designs.  `pivoting == 0` skips the search (P[k] = k).
+//
+// Kernels:
+//   lu_tpm_kernel<N>      thread-per-matrix in registers, N in {4, 8}: bulk-copy staged slabs.
+//   lu_group_kernel<G>    G threads per matrix, matrix resident in shared memory.
+//   lu_global_kernel      one CTA per matrix, in place in global memory (any N; exact; slow).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace hlsd {
+
+// Pivot candidate ordering = the reference's downward scan with a strict '<' (lu.cpp:44-52):
+// the smallest row index among the largest |a|.  NaNs below the diagonal never win; a NaN on
+// the diagonal is never displaced (every comparison with it is false).
+struct PivotCand {
+    float v;
+    int i;
+};
+__device__ __forceinline__ PivotCand pivot_better(PivotCand a, PivotCand b) {
+    return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+__device__ __forceinline__ float pivot_key(float x, bool is_diag) {
+    float v = fabsf(x);
+    if (v != v) v = is_diag ? __int_as_float(0x7f800000) : -1.0f;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// thread-per-matrix (registers), slabs staged by bulk copies as in chol_tpm_kernel
+// ------------------------------------------------------------------------------------------------
+template <int N, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+lu_tpm_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restrict__ U, int* __restrict__ P,
+              long batch, int pivoting) {
+    constexpr int kSlot = N * N + 4;
+    constexpr int kMatBytes = N * N * 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // per warp: slab for A (reused for L) and a slab for U
+    float* slabs = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * 2 * 32 * kSlot * 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* slotA = slabs + ((size_t)warp * 2 * 32 + lane) * kSlot;
+    float* slotU = slotA + 32 * kSlot;
+    uint64_t* bar = bars + warp;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const long num_slabs = (batch + 31) / 32;
+    uint32_t parity = 0;
+    for (long s = (long)blockIdx.x * WARPS + warp; s < num_slabs; s += (long)gridDim.x * WARPS) {
+        const long m0 = s * 32;
+        const int valid = (int)min(32L, batch - m0);
+        bulk_wait_read<0>();
+        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * kMatBytes);
+        __syncwarp();
+        if (lane < valid) bulk_g2s(slotA, A + (m0 + lane) * (long)(N * N), kMatBytes, bar);
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        if (lane < valid) {
+            float a[N][N];
+            const float4* s4 = reinterpret_cast<const float4*>(slotA);
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int q = 0; q < N / 4; q++) {
+                    float4 v = s4[i * (N / 4) + q];
+                    a[i][4 * q] = v.x, a[i][4 * q + 1] = v.y, a[i][4 * q + 2] = v.z, a[i][4 * q + 3] = v.w;
+                }
+            int piv[N];
+#pragma unroll
+            for (int k = 0; k < N - 1; k++) {
+                int p = k;
+                if (pivoting) {
+                    float maxpwr = fabsf(a[k][k]);
+#pragma unroll
+                    for (int i = k + 1; i < N; i++) {
+                        float v = fabsf(a[i][k]);
+                        if (maxpwr < v) {
+                            maxpwr = v;
+                            p = i;
+                        }
+                    }
+                }
+                piv[k] = p;
+                // exchange rows k and p in columns >= k (register arrays: select, no dynamic index)
+#pragma unroll
+                for (int i = k + 1; i < N; i++)
+                    if (p == i) {
+#pragma unroll
+                        for (int j = k; j < N; j++) {
+                            float t = a[i][j];
+                            a[i][j] = a[k][j];
+                            a[k][j] = t;
+                        }
+                    }
+                float diag = a[k][k];
+#pragma unroll
+                for (int i = k + 1; i < N; i++) a[i][k] = xdiv(a[i][k], diag);
+#pragma unroll
+                for (int i = k + 1; i < N; i++)
+#pragma unroll
+                    for (int j = k + 1; j < N; j++) a[i][j] = xmsub(a[i][j], a[i][k], a[k][j]);
+            }
+            piv[N - 1] = N - 1;
+            float4* l4 = reinterpret_cast<float4*>(slotA);
+            float4* u4 = reinterpret_cast<float4*>(slotU);
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int q = 0; q < N / 4; q++) {
+                    float l[4], u[4];
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        int j = 4 * q + t;
+                        l[t] = (j < i) ? a[i][j] : (j == i ? 1.0f : 0.0f);
+                        u[t] = (j >= i) ? a[i][j] : 0.0f;
+                    }
+                    l4[i * (N / 4) + q] = make_float4(l[0], l[1], l[2], l[3]);
+                    u4[i * (N / 4) + q] = make_float4(u[0], u[1], u[2], u[3]);
+                }
+            fence_async_smem();
+            bulk_s2g(L + (m0 + lane) * (long)(N * N), slotA, kMatBytes);
+            bulk_s2g(U + (m0 + lane) * (long)(N * N), slotU, kMatBytes);
+            bulk_commit();
+            int4* p4 = reinterpret_cast<int4*>(P + (m0 + lane) * (long)N);
+#pragma unroll
+            for (int q = 0; q < N / 4; q++) p4[q] = make_int4(piv[4 * q], piv[4 * q + 1], piv[4 * q + 2], piv[4 * q + 3]);
+        }
+    }
+    bulk_wait_read<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared body: elimination of one matrix `w` (leading dimension ld) by a group of G threads.
+// SYNC() must order all G threads; `red` is scratch for the pivot reduction (G/32 candidates).
+// ------------------------------------------------------------------------------------------------
+template <int G, typename SyncF>
+__device__ __forceinline__ void lu_eliminate(float* w, long ld, int n, int t, int pivoting, int* piv_out,
+                                             PivotCand* red, SyncF sync) {
+    for (int k = 0; k < n - 1; k++) {
+        int p = k;
+        if (pivoting) {
+            PivotCand c{-2.0f, 0x7fffffff};
+            for (int i = k + t; i < n; i += G) c = pivot_better(c, PivotCand{pivot_key(w[i * ld + k], i == k), i});
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                PivotCand o{__shfl_xor_sync(0xffffffffu, c.v, off), __shfl_xor_sync(0xffffffffu, c.i, off)};
+                c = pivot_better(c, o);
+            }
+            if constexpr (G > 32) {
+                if ((t & 31) == 0) red[t >> 5] = c;
+                sync();
+                c = red[0];
+#pragma unroll
+                for (int q = 1; q < G / 32; q++) c = pivot_better(c, red[q]);
+                sync();  // red is reused next step
+            }
+            p = c.i;
+        }
+        if (t == 0) piv_out[k] = p;
+        if (p != k)
+            for (int j = k + t; j < n; j += G) {
+                float tmp = w[p * ld + j];
+                w[p * ld + j] = w[k * ld + j];
+                w[k * ld + j] = tmp;
+            }
+        sync();
+        const float diag = w[k * ld + k];
+        for (int i = k + 1 + t; i < n; i += G) w[i * ld + k] = xdiv(w[i * ld + k], diag);
+        sync();
+        const int m = n - k - 1;
+        for (long e = t; e < (long)m * m; e += G) {
+            int ii = (int)(e / m), jj = (int)(e - (long)ii * m);
+            long i = k + 1 + ii, j = k + 1 + jj;
+            w[i * ld + j] = xmsub(w[i * ld + j], w[i * ld + k], w[k * ld + j]);
+        }
+        sync();
+    }
+    if (t == 0) piv_out[n - 1] = n - 1;
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+lu_group_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restrict__ U, int* __restrict__ P, int n,
+                long batch, int pivoting) {
+    extern __shared__ __align__(16) float smem_f[];
+    constexpr int kGroups = 256 / G;
+    __shared__ PivotCand red_all[8];
+    const int g = threadIdx.x / G, t = threadIdx.x % G;
+    const int ld = n | 1;
+    float* w = smem_f + (size_t)g * (size_t)n * ld;
+    PivotCand* red = red_all + g * (G / 32);
+    const long nn = (long)n * n;
+    auto sync = [g]() { group_sync<G>(g); };
+    for (long b = (long)blockIdx.x * kGroups + g; b < batch; b += (long)gridDim.x * kGroups) {
+        const float* a = A + b * nn;
+        for (int e = t; e < n * n; e += G) {
+            int i = e / n, j = e - i * n;
+            w[i * ld + j] = a[e];
+        }
+        sync();
+        lu_eliminate<G>(w, ld, n, t, pivoting, P + b * n, red, sync);
+        float* l = L + b * nn;
+        float* u = U + b * nn;
+        for (int e = t; e < n * n; e += G) {
+            int i = e / n, j = e - i * n;
+            float v = w[i * ld + j];
+            l[e] = (j < i) ? v : (j == i ? 1.0f : 0.0f);
+            u[e] = (j >= i) ? v : 0.0f;
+        }
+        sync();
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+lu_global_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restrict__ U, int* __restrict__ P, int n,
+                 long batch, int pivoting) {
+    __shared__ PivotCand red[32];
+    const int t = threadIdx.x;
+    const long nn = (long)n * n;
+    auto sync = []() { __syncthreads(); };
+    for (long b = blockIdx.x; b < batch; b += gridDim.x) {
+        const float* a = A + b * nn;
+        float* w = U + b * nn;  // eliminate in place in the U buffer, split into L and U afterwards
+        float* l = L + b * nn;
+        for (long e = t; e < nn; e += 1024) w[e] = a[e];
+        __syncthreads();
+        lu_eliminate<1024>(w, n, n, t, pivoting, P + b * n, red, sync);
+        for (long e = t; e < nn; e += 1024) {
+            int i = (int)(e / n), j = (int)(e - (long)i * n);
+            float v = w[e];
+            l[e] = (j < i) ? v : (j == i ? 1.0f : 0.0f);
+            if (j < i) w[e] = 0.0f;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int N>
+static cudaError_t launch_lu_tpm(const float* A, float* L, float* U, int* P, long batch, int pivoting, cudaStream_t st) {
+    constexpr int WARPS = 8;
+    constexpr int kSlot = N * N + 4;
+    const size_t smem = (size_t)WARPS * 2 * 32 * kSlot * 4 + WARPS * sizeof(uint64_t);
+    auto kern = lu_tpm_kernel<N, WARPS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long num_slabs = (batch + 31) / 32;
+    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024) / (smem + 1024)));
+    long grid = std::min<long>((num_slabs + WARPS - 1) / WARPS, (long)sm_count() * ctas_per_sm);
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(A, L, U, P, batch, pivoting);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int G>
+static cudaError_t launch_lu_group(const float* A, float* L, float* U, int* P, int n, long batch, int pivoting,
+                                   cudaStream_t st) {
+    constexpr int kGroups = 256 / G;
+    const size_t smem = (size_t)n * (n | 1) * 4 * kGroups;
+    auto kern = lu_group_kernel<G>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(227 * 1024) / (smem + 1024)));
+    long grid = std::min<long>((batch + kGroups - 1) / kGroups, (long)sm_count() * ctas_per_sm);
+    kern<<<(unsigned)grid, 256, smem, st>>>(A, L, U, P, n, batch, pivoting);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t lu_exact(const float* A, float* L, float* U, int* P, int n, long batch, int pivoting, int path,
+                     cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    const bool aligned = (((uintptr_t)A | (uintptr_t)L | (uintptr_t)U | (uintptr_t)P) & 15) == 0;
+    if (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM) {
+        if (aligned && n == 4) return launch_lu_tpm<4>(A, L, U, P, batch, pivoting, st);
+        if (aligned && n == 8) return launch_lu_tpm<8>(A, L, U, P, batch, pivoting, st);
+        if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
+    }
+    const size_t per = (size_t)n * (n | 1) * 4;
+    const size_t cap = 227 * 1024 - 1024;
+    if ((path == HLSD_PATH_AUTO && per <= cap) || path == HLSD_PATH_GROUP) {
+        if (per > cap) return cudaErrorInvalidValue;
+        if (n <= 48 && per * 8 <= cap) return launch_lu_group<32>(A, L, U, P, n, batch, pivoting, st);
+        if (n <= 96 && per * 2 <= cap) return launch_lu_group<128>(A, L, U, P, n, batch, pivoting, st);
+        return launch_lu_group<256>(A, L, U, P, n, batch, pivoting, st);
+    }
+    long grid = std::min<long>(batch, (long)sm_count() * 2);
+    lu_global_kernel<<<(unsigned)grid, 1024, 0, st>>>(A, L, U, P, n, batch, pivoting);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace hlsd

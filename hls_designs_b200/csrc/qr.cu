@@ -1,0 +1,320 @@
+// Batched QR by Givens rotations, the reference's `int top(A, Q, R)` (QR/qr_v*/model4x4/qr.h:22-24).
+//
+//   variant 0  qr_v2.1: per column c, rows i = ROWS-1 .. c+1, rotate adjacent rows (i-1, i); a
+//              rotation is skipped (c = 1, s = 0, still applied) when A[i] == 0
+//              (qr_v2.1/template/T_qr.cpp:63-148 angle generation, :150-223 row rotation,
+//              :225-300 Q accumulation).  A true QR: A = QR.
+//   variant 1  qr_v1.1 / qr_v1.2: rows paired (i-2, i) (column 0 finishes with (0, 1)), skip test
+//              |A[i]| < 1e-6 (qr_v1.1/model4x4/qr.cpp:45-127, 131-226, 310-404).  Reproduced for
+//              element-wise parity only: those designs do not satisfy A = QR.
+//
+// The systolic arrays run the rotations of different columns concurrently; so does variant 0 here:
+// rotation (i, c) only conflicts with rotations that share one of its rows, and the schedule
+// time(i, c) = (ROWS-1-i) + 2c orders every conflicting pair as the sequential loop does, so each
+// element sees the same operations in the same order and the result is bit-identical.
+//
+// Kernels:
+//   qr_tpm_kernel<N>     thread-per-matrix in registers, square N in {4, 8}.
+//   qr_wave_kernel<G>    G threads per matrix, R and Q resident in shared memory, wavefront schedule
+//                        (variant 0) or sequential schedule (variant 1).
+//   qr_global_kernel     one CTA per matrix, in place in global memory (any size; exact; slow).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace hlsd {
+
+// angle generation (qrf_mag + the two divisions), QR/qr_v2.1/model4x4/qr.cpp:36-43 and :96-100
+__device__ __forceinline__ void givens_make(float& lo, float& hi, bool skip, float& c, float& s) {
+    if (skip) {
+        c = 1.0f;
+        s = 0.0f;
+    } else {
+        float mag = xsqrt(xadd(xmul(hi, hi), xmul(lo, lo)));
+        c = xdiv(lo, mag);
+        s = xdiv(hi, mag);
+        lo = mag;
+        hi = 0.0f;
+    }
+}
+template <int VARIANT>
+__device__ __forceinline__ bool givens_skip(float hi) {
+    if constexpr (VARIANT == 0) return hi == 0.0f;
+    else return fabsf(hi) < 1e-6;  // double comparison, as in the reference (`1e-6` is a double literal)
+}
+
+// ------------------------------------------------------------------------------------------------
+// thread-per-matrix (registers): square N x N
+// ------------------------------------------------------------------------------------------------
+template <int N, int VARIANT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+qr_tpm_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restrict__ R, long batch) {
+    constexpr int kSlot = N * N + 4;
+    constexpr int kMatBytes = N * N * 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* slabs = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * 2 * 32 * kSlot * 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* slotR = slabs + ((size_t)warp * 2 * 32 + lane) * kSlot;
+    float* slotQ = slotR + 32 * kSlot;
+    uint64_t* bar = bars + warp;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const long num_slabs = (batch + 31) / 32;
+    uint32_t parity = 0;
+    for (long sl = (long)blockIdx.x * WARPS + warp; sl < num_slabs; sl += (long)gridDim.x * WARPS) {
+        const long m0 = sl * 32;
+        const int valid = (int)min(32L, batch - m0);
+        bulk_wait_read<0>();
+        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * kMatBytes);
+        __syncwarp();
+        if (lane < valid) bulk_g2s(slotR, A + (m0 + lane) * (long)(N * N), kMatBytes, bar);
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        if (lane < valid) {
+            float r[N][N], q[N][N];
+            const float4* s4 = reinterpret_cast<const float4*>(slotR);
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int v = 0; v < N / 4; v++) {
+                    float4 x = s4[i * (N / 4) + v];
+                    r[i][4 * v] = x.x, r[i][4 * v + 1] = x.y, r[i][4 * v + 2] = x.z, r[i][4 * v + 3] = x.w;
+                }
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int j = 0; j < N; j++) q[i][j] = (i == j) ? 1.0f : 0.0f;
+#pragma unroll
+            for (int col = 0; col < N; col++) {
+#pragma unroll
+                for (int i = N - 1; i > col; i--) {
+                    constexpr int dummy = 0;
+                    (void)dummy;
+                    const int lo = (VARIANT == 0) ? i - 1 : ((col == 0 && i < 2) ? i - 1 : i - 2);
+                    float c, s;
+                    givens_make(r[lo][col], r[i][col], givens_skip<VARIANT>(r[i][col]), c, s);
+#pragma unroll
+                    for (int j = col + 1; j < N; j++) givens_apply(c, s, r[lo][j], r[i][j]);
+#pragma unroll
+                    for (int k = 0; k < N; k++) givens_apply(c, s, q[k][lo], q[k][i]);
+                }
+            }
+            float4* r4 = reinterpret_cast<float4*>(slotR);
+            float4* q4 = reinterpret_cast<float4*>(slotQ);
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int v = 0; v < N / 4; v++) {
+                    r4[i * (N / 4) + v] = make_float4(r[i][4 * v], r[i][4 * v + 1], r[i][4 * v + 2], r[i][4 * v + 3]);
+                    q4[i * (N / 4) + v] = make_float4(q[i][4 * v], q[i][4 * v + 1], q[i][4 * v + 2], q[i][4 * v + 3]);
+                }
+            fence_async_smem();
+            bulk_s2g(R + (m0 + lane) * (long)(N * N), slotR, kMatBytes);
+            bulk_s2g(Q + (m0 + lane) * (long)(N * N), slotQ, kMatBytes);
+            bulk_commit();
+        }
+    }
+    bulk_wait_read<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared body: factor one matrix held in r (rows x ldr) / q (rows x ldq) with G threads.
+// cs: scratch for 2 * (rows/2 + 1) floats (the (c, s) pairs of one wavefront).
+// ------------------------------------------------------------------------------------------------
+template <int G, int VARIANT, typename SyncF>
+__device__ __forceinline__ void qr_factor(float* r, long ldr, float* q, long ldq, int rows, int cols, int t, float* cs,
+                                          SyncF sync) {
+    if constexpr (VARIANT == 0) {
+        const int last_t = (rows - 1) + 2 * (cols - 1);  // generous bound; empty steps are skipped
+        for (int step = 0; step <= last_t; step++) {
+            // rotations of this step: columns c with i = rows-1-step+2c, c < i <= rows-1, c < cols
+            int c_lo = max(0, step - rows + 2);
+            int c_hi = min(cols - 1, step / 2);
+            const int nrot = c_hi - c_lo + 1;
+            if (nrot <= 0) continue;
+            for (int k = t; k < nrot; k += G) {
+                const int c = c_lo + k, i = rows - 1 - step + 2 * c;
+                float lo = r[(long)(i - 1) * ldr + c], hi = r[(long)i * ldr + c];
+                float cc, ss;
+                const bool skip = givens_skip<0>(hi);
+                givens_make(lo, hi, skip, cc, ss);
+                r[(long)(i - 1) * ldr + c] = lo;
+                r[(long)i * ldr + c] = hi;
+                cs[2 * k] = cc;
+                cs[2 * k + 1] = ss;
+            }
+            sync();
+            const int width = cols + rows;
+            for (int k = 0; k < nrot; k++) {
+                const int c = c_lo + k, i = rows - 1 - step + 2 * c;
+                const float cc = cs[2 * k], ss = cs[2 * k + 1];
+                for (int x = t; x < width; x += G) {
+                    if (x < cols) {
+                        if (x > c) givens_apply(cc, ss, r[(long)(i - 1) * ldr + x], r[(long)i * ldr + x]);
+                    } else {
+                        const int row = x - cols;
+                        givens_apply(cc, ss, q[(long)row * ldq + (i - 1)], q[(long)row * ldq + i]);
+                    }
+                }
+            }
+            sync();
+        }
+    } else {
+        for (int col = 0; col < cols; col++)
+            for (int i = rows - 1; i > col; i--) {
+                const int lo_row = (col == 0 && i < 2) ? i - 1 : i - 2;
+                float lo = r[(long)lo_row * ldr + col], hi = r[(long)i * ldr + col];
+                float cc, ss;
+                givens_make(lo, hi, givens_skip<1>(hi), cc, ss);
+                sync();  // every thread has read the generating pair
+                if (t == 0) {
+                    r[(long)lo_row * ldr + col] = lo;
+                    r[(long)i * ldr + col] = hi;
+                }
+                const int width = cols + rows;
+                for (int x = t; x < width; x += G) {
+                    if (x < cols) {
+                        if (x > col) givens_apply(cc, ss, r[(long)lo_row * ldr + x], r[(long)i * ldr + x]);
+                    } else {
+                        const int row = x - cols;
+                        givens_apply(cc, ss, q[(long)row * ldq + lo_row], q[(long)row * ldq + i]);
+                    }
+                }
+                sync();
+            }
+    }
+}
+
+template <int G, int VARIANT>
+__global__ void __launch_bounds__(256)
+qr_wave_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restrict__ R, int rows, int cols,
+               long batch) {
+    extern __shared__ __align__(16) float smem_f[];
+    constexpr int kGroups = 256 / G;
+    const int g = threadIdx.x / G, t = threadIdx.x % G;
+    const int ldr = cols | 1, ldq = rows | 1;
+    const size_t per = (size_t)rows * ldr + (size_t)rows * ldq + 2 * (rows / 2 + 2);
+    float* r = smem_f + g * per;
+    float* q = r + (size_t)rows * ldr;
+    float* cs = q + (size_t)rows * ldq;
+    auto sync = [g]() { group_sync<G>(g); };
+    const long na = (long)rows * cols, nq = (long)rows * rows;
+    for (long b = (long)blockIdx.x * kGroups + g; b < batch; b += (long)gridDim.x * kGroups) {
+        const float* a = A + b * na;
+        for (int e = t; e < rows * cols; e += G) {
+            int i = e / cols, j = e - i * cols;
+            r[i * ldr + j] = a[e];
+        }
+        for (int e = t; e < rows * rows; e += G) {
+            int i = e / rows, j = e - i * rows;
+            q[i * ldq + j] = (i == j) ? 1.0f : 0.0f;
+        }
+        sync();
+        qr_factor<G, VARIANT>(r, ldr, q, ldq, rows, cols, t, cs, sync);
+        float* ro = R + b * na;
+        float* qo = Q + b * nq;
+        for (int e = t; e < rows * cols; e += G) {
+            int i = e / cols, j = e - i * cols;
+            ro[e] = r[i * ldr + j];
+        }
+        for (int e = t; e < rows * rows; e += G) {
+            int i = e / rows, j = e - i * rows;
+            qo[e] = q[i * ldq + j];
+        }
+        sync();
+    }
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(1024)
+qr_global_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restrict__ R, int rows, int cols,
+                 long batch) {
+    extern __shared__ __align__(16) float cs[];
+    const int t = threadIdx.x;
+    auto sync = []() { __syncthreads(); };
+    const long na = (long)rows * cols, nq = (long)rows * rows;
+    for (long b = blockIdx.x; b < batch; b += gridDim.x) {
+        const float* a = A + b * na;
+        float* r = R + b * na;
+        float* q = Q + b * nq;
+        for (long e = t; e < na; e += 1024) r[e] = a[e];
+        for (long e = t; e < nq; e += 1024) {
+            int i = (int)(e / rows), j = (int)(e - (long)i * rows);
+            q[e] = (i == j) ? 1.0f : 0.0f;
+        }
+        __syncthreads();
+        qr_factor<1024, VARIANT>(r, cols, q, rows, rows, cols, t, cs, sync);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int N, int VARIANT>
+static cudaError_t launch_qr_tpm(const float* A, float* Q, float* R, long batch, cudaStream_t st) {
+    constexpr int WARPS = (N == 8) ? 4 : 8;
+    constexpr int kSlot = N * N + 4;
+    const size_t smem = (size_t)WARPS * 2 * 32 * kSlot * 4 + WARPS * sizeof(uint64_t);
+    auto kern = qr_tpm_kernel<N, VARIANT, WARPS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long num_slabs = (batch + 31) / 32;
+    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024) / (smem + 1024)));
+    long grid = std::min<long>((num_slabs + WARPS - 1) / WARPS, (long)sm_count() * ctas_per_sm);
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(A, Q, R, batch);
+    count_launch();
+    return cudaGetLastError();
+}
+
+static size_t qr_smem_per_matrix(int rows, int cols) {
+    return ((size_t)rows * (cols | 1) + (size_t)rows * (rows | 1) + 2 * (rows / 2 + 2)) * 4;
+}
+
+template <int G, int VARIANT>
+static cudaError_t launch_qr_wave(const float* A, float* Q, float* R, int rows, int cols, long batch, cudaStream_t st) {
+    constexpr int kGroups = 256 / G;
+    const size_t smem = qr_smem_per_matrix(rows, cols) * kGroups;
+    auto kern = qr_wave_kernel<G, VARIANT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(227 * 1024) / (smem + 1024)));
+    long grid = std::min<long>((batch + kGroups - 1) / kGroups, (long)sm_count() * ctas_per_sm);
+    kern<<<(unsigned)grid, 256, smem, st>>>(A, Q, R, rows, cols, batch);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int VARIANT>
+static cudaError_t qr_dispatch(const float* A, float* Q, float* R, int rows, int cols, long batch, int path,
+                               cudaStream_t st) {
+    const bool aligned = (((uintptr_t)A | (uintptr_t)Q | (uintptr_t)R) & 15) == 0;
+    if (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM) {
+        if (aligned && rows == 4 && cols == 4) return launch_qr_tpm<4, VARIANT>(A, Q, R, batch, st);
+        if (aligned && rows == 8 && cols == 8) return launch_qr_tpm<8, VARIANT>(A, Q, R, batch, st);
+        if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
+    }
+    const size_t per = qr_smem_per_matrix(rows, cols);
+    const size_t cap = 227 * 1024 - 1024;
+    if ((path == HLSD_PATH_AUTO && per <= cap) || path == HLSD_PATH_GROUP) {
+        if (per > cap) return cudaErrorInvalidValue;
+        if (rows <= 32 && per * 8 <= cap) return launch_qr_wave<32, VARIANT>(A, Q, R, rows, cols, batch, st);
+        if (rows <= 64 && per * 2 <= cap) return launch_qr_wave<128, VARIANT>(A, Q, R, rows, cols, batch, st);
+        return launch_qr_wave<256, VARIANT>(A, Q, R, rows, cols, batch, st);
+    }
+    long grid = std::min<long>(batch, (long)sm_count() * 2);
+    const size_t smem = (size_t)(2 * (rows / 2 + 2)) * 4;
+    qr_global_kernel<VARIANT><<<(unsigned)grid, 1024, smem, st>>>(A, Q, R, rows, cols, batch);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t qr_exact(const float* A, float* Q, float* R, int rows, int cols, long batch, int variant, int path,
+                     cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    return variant == 1 ? qr_dispatch<1>(A, Q, R, rows, cols, batch, path, st)
+                        : qr_dispatch<0>(A, Q, R, rows, cols, batch, path, st);
+}
+
+}  // namespace hlsd

@@ -1,0 +1,100 @@
+/* hlsd.h — C ABI of libhlsd.so: batched Cholesky / LU / Givens-QR on NVIDIA B200 (sm_100a).
+ *
+ * Drop-in boundary for the top-level functions of Sibylau/HLS_designs.  Each reference design is
+ * a fixed-size function over row-major float arrays:
+ *
+ *   int top(matrix_t A[N][N], matrix_t L[N][N]);                               Cholesky
+ *       Cholesky/cholesky_v{1.3,2.2,3.2,4.0}/model4x4/chol.h:15-16
+ *   int top(matrix_t A[N][N], matrix_t L[N][N], matrix_t U[N][N], uint_i P[N]); LU
+ *       LU/lu_v{1.1,1.2,2.1}/model4x4/lu.h:19-22
+ *   int top(MATRIX_T A[ROWS][COLS], MATRIX_T Q[ROWS][ROWS], MATRIX_T R[ROWS][COLS]); QR
+ *       QR/qr_v{1.1,1.2,2.1}/model4x4/qr.h:22-24
+ *
+ * The entry points below are those functions with the compile-time size turned into arguments
+ * and a leading batch dimension added: matrix b of a batch starts at base + b*rows*cols floats,
+ * every matrix row-major exactly as `matrix_t A[N][N]` (and as the op<N>.bin / op<M>x<N>.bin
+ * operand files once read with fread(A[i], sizeof(float), N, fp), e.g. chol_tb.cpp:18-24).
+ * Output layouts are the reference collectors': L lower triangular with zeros above the diagonal
+ * (unit diagonal for LU), U upper triangular with zeros below, P[k] = row exchanged with row k at
+ * step k (P[N-1] = N-1), Q ROWSxROWS, R ROWSxCOLS.
+ *
+ * `*_host` functions take HOST pointers (like the reference's top()): they copy in, run, copy out
+ * and return when the outputs are complete.  `*_dev` functions take DEVICE pointers and a
+ * cudaStream_t (as void*) and only enqueue work.  All return 0 on success (like top()) or an
+ * hlsd_status; hlsd_last_error() describes the last failure of the calling thread.
+ * There is no CPU implementation behind this interface.
+ */
+#ifndef HLSD_H
+#define HLSD_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    HLSD_OK = 0,
+    HLSD_ERR_INVALID = 1,     /* bad size / null pointer / unknown design or flag */
+    HLSD_ERR_CUDA = 2,        /* a CUDA call failed; see hlsd_last_error() */
+    HLSD_ERR_UNSUPPORTED = 3  /* valid request this build cannot serve (e.g. forced path does not fit) */
+} hlsd_status;
+
+/* Which reference design's arithmetic to reproduce (results are element-wise identical to that
+ * design's C-simulation on the exact paths). */
+typedef enum {
+    HLSD_CHOL_V1_3 = 13, /* right-looking 1-D array            cholesky_v1.3/model4x4/chol.cpp:25-63   */
+    HLSD_CHOL_V2_2 = 22, /* revised, roots taken at the end     cholesky_v2.2/model4x4/chol.cpp:28-207  */
+    HLSD_CHOL_V3_2 = 32, /* 2-D array (== v1.3 arithmetic)      cholesky_v3.2/model4x4/chol.cpp:94-181  */
+    HLSD_CHOL_V4_0 = 40  /* 1-D, other projection (== v1.3)     cholesky_v4.0/model4x4/chol.cpp:64-130  */
+} hlsd_chol_design;
+
+typedef enum {
+    HLSD_LU_V1_1 = 11, /* Doolittle, partial pivoting, 1-D     lu_v1.1/model4x4/lu.cpp:23-92   */
+    HLSD_LU_V1_2 = 12, /* same arithmetic, other projection    lu_v1.2/model4x4/lu.cpp:75-167  */
+    HLSD_LU_V2_1 = 21, /* same arithmetic, 2-D array           lu_v2.1/model4x4/lu.cpp:50-155  */
+    HLSD_LU_NOPIVOT = 1 /* this library's unpivoted variant: same elimination, P[k] = k always */
+} hlsd_lu_design;
+
+typedef enum {
+    HLSD_QR_V1_1 = 11, /* 1-D array, rows paired (i-2, i)      qr_v1.1/model4x4/qr.cpp:45-308 (A != QR: reference defect) */
+    HLSD_QR_V1_2 = 12, /* == v1.1 arithmetic                   qr_v1.2/model4x4/qr.cpp                                    */
+    HLSD_QR_V2_1 = 21  /* 2-D array, adjacent rows (i-1, i)    qr_v2.1/template/T_qr.cpp:63-300                           */
+} hlsd_qr_design;
+
+/* flags: low byte selects the kernel family (0 = automatic by size). */
+#define HLSD_PATH_AUTO 0
+#define HLSD_PATH_TPM 1     /* thread-per-matrix, register resident (N in {4, 8, 16})        */
+#define HLSD_PATH_GROUP 2   /* warp/CTA per matrix, shared-memory resident                     */
+#define HLSD_PATH_GLOBAL 3  /* one CTA per matrix in global memory: any N, exact, slow         */
+#define HLSD_PATH_BLOCKED 4 /* blocked right-looking, fp32 SIMT trailing update (exact order)  */
+#define HLSD_PATH_TENSOR 5  /* blocked right-looking, tcgen05 tensor-core trailing update      */
+#define HLSD_PATH_MASK 0xff
+
+/* ---- host-pointer entry points (the reference's top(), batched) ---- */
+int hlsd_cholesky_host(const float* A, float* L, int n, int64_t batch, int design, int flags);
+int hlsd_lu_host(const float* A, float* L, float* U, int32_t* P, int n, int64_t batch, int design, int flags);
+int hlsd_qr_host(const float* A, float* Q, float* R, int rows, int cols, int64_t batch, int design, int flags);
+
+/* ---- device-pointer entry points (enqueue on `stream`, a cudaStream_t; NULL = default stream) ---- */
+int hlsd_cholesky_dev(const float* dA, float* dL, int n, int64_t batch, int design, int flags, void* stream);
+int hlsd_lu_dev(const float* dA, float* dL, float* dU, int32_t* dP, int n, int64_t batch, int design, int flags,
+                void* stream);
+int hlsd_qr_dev(const float* dA, float* dQ, float* dR, int rows, int cols, int64_t batch, int design, int flags,
+                void* stream);
+
+/* ---- pinned host buffers for the *_host entry points (optional; pageable memory also works) ---- */
+void* hlsd_host_alloc(size_t bytes);
+void hlsd_host_free(void* p);
+
+/* ---- housekeeping ---- */
+int hlsd_set_device(int device);           /* cudaSetDevice for the calling thread */
+int hlsd_device_count(void);
+int64_t hlsd_launch_count(void);           /* kernels launched by this library so far (process-wide) */
+const char* hlsd_last_error(void);         /* thread-local, never NULL */
+const char* hlsd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HLSD_H */

@@ -81,9 +81,16 @@ def build_one(design, tag, src_dir, stem, with_tb=True):
     return lib
 
 
+FORCE = False
+
+
 def job(design, size):
     algo, stem, _ = DESIGNS[design]
     ddir = os.path.join(REF, algo, design)
+    tag0 = size if isinstance(size, str) else (f"{size[0]}x{size[1]}" if isinstance(size, tuple) else str(size))
+    lib0 = os.path.join(OUT, f"lib{design}_{tag0}.so")
+    if not FORCE and os.path.exists(lib0) and os.path.getmtime(lib0) >= os.path.getmtime(os.path.join(HERE, "ref_wrap.cpp")):
+        return lib0  # already built (the reference tree is read-only and does not change)
     if size == "model4x4":
         return build_one(design, "model4x4", os.path.join(ddir, "model4x4"), stem)
     if stem == "qr":
@@ -107,7 +114,9 @@ def main():
         print(f"build_ref: {REF} not present; keeping prebuilt oracle/_ref as is")
         return 0
     os.makedirs(GEN, exist_ok=True)
-    only = set(sys.argv[1:])
+    global FORCE
+    FORCE = "--force" in sys.argv
+    only = set(a for a in sys.argv[1:] if not a.startswith("--"))
     jobs = []
     for design, (algo, stem, one_d) in DESIGNS.items():
         if only and design not in only:

@@ -1,0 +1,85 @@
+import os
+import resource
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+# the reference's PE functions keep N x N float arrays on the stack (oracle/_ref only)
+try:
+    resource.setrlimit(resource.RLIMIT_STACK, (resource.RLIM_INFINITY, resource.RLIM_INFINITY))
+except (ValueError, OSError):
+    pass
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="session")
+def golden_chol():
+    return np.load(os.path.join(GOLDEN, "golden_chol.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_lu():
+    return np.load(os.path.join(GOLDEN, "golden_lu.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_qr():
+    return np.load(os.path.join(GOLDEN, "golden_qr.npz"))
+
+
+def bits_equal(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    if a.shape != b.shape or a.dtype != b.dtype:
+        return False
+    if a.dtype == np.float32:
+        return np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    return np.array_equal(a, b)
+
+
+def first_mismatch(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    bad = np.argwhere(a.view(np.uint32) != b.view(np.uint32)) if a.dtype == np.float32 else np.argwhere(a != b)
+    if len(bad) == 0:
+        return "identical"
+    idx = tuple(bad[0])
+    return f"{len(bad)} of {a.size} differ; first at {idx}: {a[idx]!r} vs {b[idx]!r}"
+
+
+# ---- float64 reconstruction helpers (residuals named by BASELINE.json's north_star) -------------
+def chol_residual(A, L):
+    A64, L64 = A.astype(np.float64), L.astype(np.float64)
+    return np.linalg.norm(A64 - L64 @ np.swapaxes(L64, -1, -2), axis=(-2, -1)) / np.linalg.norm(A64, axis=(-2, -1))
+
+
+def lu_reconstruct(L, U, P):
+    """Undo the reference's LINPACK-style elimination: at step k rows k and P[k] were exchanged in
+    the trailing columns only, then multiples of row k subtracted (lu_v1.1/model4x4/lu.cpp:44-91)."""
+    L64, X = L.astype(np.float64), U.astype(np.float64).copy()
+    n = X.shape[-1]
+    for k in range(n - 2, -1, -1):
+        X[k + 1:, :] += np.outer(L64[k + 1:, k], X[k, :])
+        p = int(P[k])
+        if p != k:
+            X[[k, p], :] = X[[p, k], :]
+    return X
+
+
+def lu_residual(A, L, U, P):
+    A64 = A.astype(np.float64)
+    return np.linalg.norm(A64 - lu_reconstruct(L, U, P)) / np.linalg.norm(A64)
+
+
+def qr_residual(A, Q, R):
+    A64 = A.astype(np.float64)
+    return np.linalg.norm(A64 - Q.astype(np.float64) @ R.astype(np.float64), axis=(-2, -1)) / np.linalg.norm(A64, axis=(-2, -1))

@@ -1,0 +1,170 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+libhlsd.so (host-pointer entry points with numpy buffers, device-pointer entry points with torch
+tensors) and is compared BIT FOR BIT with the oracle (oracle/restate.c, itself pinned against the
+reference's own code) and with the golden outputs recorded from the reference."""
+import numpy as np
+import pytest
+
+import hls_designs_b200 as hd
+import restate
+from conftest import bits_equal, chol_residual, first_mismatch, lu_residual, qr_residual
+from hls_designs_b200.operand import gen_full_rank, gen_spd
+
+pytestmark = pytest.mark.gpu
+
+CHOL_DESIGNS = ("cholesky_v1.3", "cholesky_v2.2", "cholesky_v3.2", "cholesky_v4.0")
+LU_DESIGNS = ("lu_v1.1", "lu_v1.2", "lu_v2.1")
+QR_DESIGNS = ("qr_v1.1", "qr_v1.2", "qr_v2.1")
+
+
+def _paths_for(n, kind):
+    paths = ["auto", "group", "global"]
+    if (kind == "chol" and n in (4, 8, 16)) or (kind in ("lu", "qr") and n in (4, 8)):
+        paths.append("tpm")
+    return paths
+
+
+# ---------------------------------------------------------------- golden (reference csim outputs)
+@pytest.mark.parametrize("n", (4, 8, 16, 25, 32, 64, 128))
+def test_cholesky_golden(golden_chol, n):
+    A = golden_chol[f"A_{n}"]
+    for d in CHOL_DESIGNS:
+        key = f"L_{d}_{n}"
+        if key not in golden_chol:
+            continue
+        for path in _paths_for(n, "chol"):
+            L = hd.cholesky(A, design=d, path=path)
+            assert bits_equal(L, golden_chol[key]), f"{d} n={n} path={path}: {first_mismatch(L, golden_chol[key])}"
+
+
+@pytest.mark.parametrize("n", (4, 6, 8, 16, 32, 64, 128))
+def test_lu_golden(golden_lu, n):
+    A = golden_lu[f"A_{n}"]
+    for d in LU_DESIGNS:
+        if f"L_{d}_{n}" not in golden_lu:
+            continue
+        for path in _paths_for(n, "lu"):
+            L, U, P = hd.lu(A, design=d, path=path)
+            assert bits_equal(L, golden_lu[f"L_{d}_{n}"]), f"L {d} n={n} {path}: {first_mismatch(L, golden_lu[f'L_{d}_{n}'])}"
+            assert bits_equal(U, golden_lu[f"U_{d}_{n}"]), f"U {d} n={n} {path}: {first_mismatch(U, golden_lu[f'U_{d}_{n}'])}"
+            assert np.array_equal(P, golden_lu[f"P_{d}_{n}"]), f"P {d} n={n} {path}"
+
+
+@pytest.mark.parametrize("shape", ((4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (128, 128), (8, 4), (16, 8), (12, 5)))
+def test_qr_golden(golden_qr, shape):
+    tag = f"{shape[0]}x{shape[1]}"
+    A = golden_qr[f"A_{tag}"]
+    for d in QR_DESIGNS:
+        if f"Q_{d}_{tag}" not in golden_qr:
+            continue
+        for path in _paths_for(shape[0] if shape[0] == shape[1] else 0, "qr"):
+            Q, R = hd.qr(A, design=d, path=path)
+            assert bits_equal(Q, golden_qr[f"Q_{d}_{tag}"]), f"Q {d} {tag} {path}: {first_mismatch(Q, golden_qr[f'Q_{d}_{tag}'])}"
+            assert bits_equal(R, golden_qr[f"R_{d}_{tag}"]), f"R {d} {tag} {path}: {first_mismatch(R, golden_qr[f'R_{d}_{tag}'])}"
+
+
+# ---------------------------------------------------------------- seeded batches vs the oracle
+@pytest.mark.parametrize("n,batch", ((4, 1000), (8, 777), (16, 4099), (16, 31), (5, 70), (25, 40), (32, 300), (48, 64),
+                                     (64, 200), (100, 9), (128, 20), (200, 3)))
+def test_cholesky_batches_vs_oracle(n, batch):
+    A = gen_spd(n, batch=batch, seed=n * 1000 + batch)
+    for d in ("cholesky_v1.3", "cholesky_v2.2"):
+        want = restate.cholesky(A, d, threads=8)
+        got = hd.cholesky(A, design=d)
+        assert bits_equal(got, want), f"{d} n={n}: {first_mismatch(got, want)}"
+    assert chol_residual(A, got).max() < 2e-6
+
+
+@pytest.mark.parametrize("n,batch", ((4, 1000), (6, 50), (8, 777), (16, 500), (17, 33), (32, 300), (64, 130), (96, 10),
+                                     (128, 12), (230, 3)))
+def test_lu_batches_vs_oracle(n, batch):
+    rng = np.random.default_rng(n)
+    for A in (gen_full_rank(n, batch=batch, seed=n + batch),
+              (rng.standard_normal((batch, n, n)) * 2).astype(np.float32)):
+        for design, piv in (("lu_v1.1", True), ("nopivot", False)):
+            want = restate.lu(A, pivoting=piv, threads=8)
+            got = hd.lu(A, design=design)
+            for name, g, w in zip("LUP", got, want):
+                assert bits_equal(g, w), f"{name} {design} n={n}: {first_mismatch(g, w)}"
+    L, U, P = hd.lu(A[:2], design="lu_v2.1")
+    assert lu_residual(A[0], L[0], U[0], P[0]) < 5e-5
+
+
+@pytest.mark.parametrize("rows,cols,batch", ((4, 4, 500), (8, 8, 300), (8, 4, 100), (12, 5, 64), (16, 16, 200),
+                                             (32, 32, 100), (33, 20, 17), (64, 64, 40), (128, 128, 6), (128, 64, 5),
+                                             (160, 160, 2)))
+def test_qr_batches_vs_oracle(rows, cols, batch):
+    A = gen_full_rank(rows, cols, batch=batch, seed=rows * cols + batch)
+    A[0, rows - 1, 0] = 0.0  # exercise the "already zero" branch (c = 1, s = 0)
+    for d in ("qr_v2.1", "qr_v1.1"):
+        want = restate.qr(A, d, threads=8)
+        got = hd.qr(A, design=d)
+        for name, g, w in zip("QR", got, want):
+            assert bits_equal(g, w), f"{name} {d} {rows}x{cols}: {first_mismatch(g, w)}"
+    Q, R = hd.qr(A, design="qr_v2.1")
+    assert qr_residual(A, Q, R).max() < 1e-5
+    assert np.abs(np.tril(R, -1)).max() == 0.0
+
+
+# ---------------------------------------------------------------- device-pointer entry points
+def test_device_entry_points_match_host_entry_points():
+    import torch
+    A = gen_spd(16, batch=1025, seed=1)
+    Ld = hd.cholesky(torch.from_numpy(A).cuda())
+    torch.cuda.synchronize()
+    assert bits_equal(Ld.cpu().numpy(), hd.cholesky(A))
+    B = gen_full_rank(32, batch=65, seed=2)
+    out_d = hd.lu(torch.from_numpy(B).cuda())
+    out_h = hd.lu(B)
+    for g, w in zip(out_d, out_h):
+        assert bits_equal(g.cpu().numpy(), w)
+    C = gen_full_rank(24, 16, batch=33, seed=3)
+    Qd, Rd = hd.qr(torch.from_numpy(C).cuda())
+    Qh, Rh = hd.qr(C)
+    assert bits_equal(Qd.cpu().numpy(), Qh) and bits_equal(Rd.cpu().numpy(), Rh)
+    assert hd.launch_count() > 0
+
+
+# ---------------------------------------------------------------- edges
+def test_edge_cases():
+    assert hd.cholesky(np.zeros((0, 16, 16), np.float32)).shape == (0, 16, 16)
+    assert hd.cholesky(np.array([[4.0]], np.float32))[0, 0] == 2.0
+    L, U, P = hd.lu(np.array([[0.0, 1.0], [2.0, 3.0]], np.float32))
+    assert list(P) == [1, 1] and U[0, 0] == 2.0
+    # not positive definite: NaNs exactly where the reference's csim produces them
+    A = gen_spd(16, batch=40, seed=5)
+    A[3, 5, 5] = -1.0
+    for path in ("tpm", "group", "global"):
+        got = hd.cholesky(A, path=path)
+        want = restate.cholesky(A)
+        assert bits_equal(np.isnan(got), np.isnan(want)) and np.isnan(got[3]).any()
+        ok = ~np.isnan(want)
+        assert bits_equal(got[ok], want[ok])
+    # singular / tie pivots
+    B = gen_full_rank(8, batch=64, seed=6)
+    B[1, :, 0] = 0.0
+    B[2, 3, :] = B[2, 2, :]
+    got, want = hd.lu(B), restate.lu(B)
+    assert np.array_equal(got[2], want[2])
+    with pytest.raises(hd.HlsdError):
+        hd.cholesky(gen_spd(32), path="tpm")  # forced path that cannot serve the size
+    with pytest.raises(hd.HlsdError):
+        hd.qr(np.ones((3, 5), np.float32))
+
+
+# ---------------------------------------------------------------- BASELINE.json full sizes, by property
+def test_full_size_cholesky_n16_batch_1m_properties():
+    """configs[1]: batched Cholesky fp32 N=16, batch 1M.  Residual on the device for every matrix,
+    bit-exact spot check of 4096 matrices spread over the batch against the oracle."""
+    import torch
+    batch = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.rand((batch, 16, 16), generator=g, device="cuda")
+    A = 0.5 * (A + A.transpose(1, 2)) + 16.0 * torch.eye(16, device="cuda")
+    L = hd.cholesky(A)
+    res = (A - L @ L.transpose(1, 2)).flatten(1).norm(dim=1) / A.flatten(1).norm(dim=1)
+    assert float(res.max()) < 2e-6
+    assert float(torch.triu(L, 1).abs().max()) == 0.0
+    idx = torch.arange(0, batch, batch // 4096, device="cuda")
+    want = restate.cholesky(A[idx].cpu().numpy(), threads=8)
+    assert bits_equal(L[idx].cpu().numpy(), want)
