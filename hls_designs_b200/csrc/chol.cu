@@ -12,6 +12,8 @@
 //                        back with bulk stores.  HBM-bound (2*N*N*4 bytes per matrix).
 //   chol_group_kernel<G> G threads per matrix, matrix resident in shared memory: any N that fits.
 //   chol_global_kernel   one CTA per matrix, working in place in global memory/L2: any N (slow, exact).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -123,6 +125,136 @@ chol_tpm_kernel(const float* __restrict__ A, float* __restrict__ L, long batch) 
                 }
             fence_async_smem();
             bulk_s2g(L + (m0 + lane) * (long)(N * N), slot, Cfg::kMatBytes);
+            bulk_commit();
+        }
+    }
+    bulk_wait_read<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// R lanes per matrix (R = 2 or 4), rows dealt round-robin to the lanes of a group: row i lives in
+// lane (i % R) as local row i / R.  Same bulk-copy slab staging as above, but a warp holds 32/R
+// matrices, so slabs and register files are R times smaller and R times as many warps fit on an
+// SM: the kernel is occupancy-bound (measured: 4/5/6 warps per SM -> 56/70/75 % of the HBM
+// roofline with one thread per matrix).  Per step k the owner lane roots the pivot and broadcasts
+// it by shuffle (the systolic "pivot broadcast"), every lane scales its own entries of column k,
+// and the column is all-gathered by one shuffle per row (the "column update" stream).
+// Entries a[t][j] with j > row index are scratch (computed, never stored).
+// ------------------------------------------------------------------------------------------------
+template <int N, int R, int VARIANT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+chol_rows_kernel(const float* __restrict__ A, float* __restrict__ L, long batch) {
+    using Cfg = TpmCfg<N>;
+    constexpr int MPW = 32 / R;  // matrices per warp
+    constexpr int T = N / R;     // local rows per lane
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* slabs = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * MPW * Cfg::kSlot * 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = lane % R, m = lane / R, gbase = lane - r;
+    float* slot = slabs + ((size_t)warp * MPW + m) * Cfg::kSlot;
+    uint64_t* bar = bars + warp;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const long num_slabs = (batch + MPW - 1) / MPW;
+    constexpr uint32_t kPart = Cfg::kMatBytes / R;  // each lane of a group moves 1/R of the matrix
+    uint32_t parity = 0;
+    for (long s = (long)blockIdx.x * WARPS + warp; s < num_slabs; s += (long)gridDim.x * WARPS) {
+        const long m0 = s * MPW;
+        const int valid = (int)min((long)MPW, batch - m0);
+        bulk_wait_read<0>();
+        __syncwarp();  // all lanes' previous stores have drained before anyone refills the slab
+        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * Cfg::kMatBytes);
+        __syncwarp();
+        if (m < valid)
+            bulk_g2s(slot + r * (kPart / 4), A + (m0 + m) * (long)(N * N) + r * (kPart / 4), kPart, bar);
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        // a[t][j]: row i = t*R + r, columns 0 .. t*R + R - 1 (static bound; j > i is scratch)
+        float a[T][N];
+        {
+            const float4* s4 = reinterpret_cast<const float4*>(slot);
+#pragma unroll
+            for (int t = 0; t < T; t++) {
+#pragma unroll
+                for (int q = 0; q < (t * R + R + 3) / 4; q++) {
+                    float4 v = s4[(t * R + r) * (N / 4) + q];
+                    a[t][4 * q] = v.x, a[t][4 * q + 1] = v.y, a[t][4 * q + 2] = v.z, a[t][4 * q + 3] = v.w;
+                }
+            }
+        }
+        float dsave[VARIANT == 1 ? N : 1];
+        static_for<0, N>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            constexpr int tk = k / R, rk = k % R;
+            // pivot: owner lane rk, local row tk
+            float piv = a[tk][k];
+            if constexpr (VARIANT == 0) piv = xsqrt(piv);
+            const float d = __shfl_sync(0xffffffffu, piv, gbase + rk);
+            if constexpr (VARIANT == 0) {
+                if (r == rk) a[tk][k] = d;
+            } else {
+                dsave[k] = d;
+            }
+            // own entries of column k below the diagonal: rows i = t*R + r > k
+            float own[T];
+#pragma unroll
+            for (int t = tk; t < T; t++) {
+                own[t] = xdiv(a[t][k], d);
+                if constexpr (VARIANT == 0) {
+                    if (t > tk || r > rk) a[t][k] = own[t];
+                }
+            }
+            // all-gather column k (rows k+1 .. N-1) and update
+#pragma unroll
+            for (int i = k + 1; i < N; i++) {
+                const float lik = __shfl_sync(0xffffffffu, own[i / R], gbase + (i % R));
+                // rows j = t*R + r >= i  <=>  t >= i/R (the t == i/R case is scratch when r < i % R)
+#pragma unroll
+                for (int t = i / R; t < T; t++) a[t][i] = xmsub(a[t][i], a[t][k], lik);
+            }
+            if constexpr (VARIANT == 1) {
+#pragma unroll
+                for (int t = tk; t < T; t++)
+                    if (t > tk || r > rk) a[t][k] = own[t];
+            }
+        });
+        if constexpr (VARIANT == 1) {
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+                const float rt = xsqrt(dsave[k]);
+                const int tk = k / R, rk = k % R;
+#pragma unroll
+                for (int t = tk; t < T; t++) {
+                    if (t > tk || r > rk) a[t][k] = xmul(a[t][k], rt);
+                    else if (t == tk && r == rk) a[t][k] = rt;
+                }
+            }
+        }
+        if (m < valid) {
+            float4* d4 = reinterpret_cast<float4*>(slot);
+#pragma unroll
+            for (int t = 0; t < T; t++) {
+                const int i = t * R + r;
+#pragma unroll
+                for (int q = 0; q < N / 4; q++) {
+                    float e[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int j = 4 * q + u;
+                        e[u] = (j < t * R + R && j <= i) ? a[t][j < t * R + R ? j : 0] : 0.0f;
+                    }
+                    d4[i * (N / 4) + q] = make_float4(e[0], e[1], e[2], e[3]);
+                }
+            }
+            fence_async_smem();
+        }
+        __syncwarp();  // the whole matrix (all R lanes' rows) is in the slot
+        if (m < valid) {
+            bulk_s2g(L + (m0 + m) * (long)(N * N) + r * (kPart / 4), slot + r * (kPart / 4), kPart);
             bulk_commit();
         }
     }
@@ -267,9 +399,19 @@ chol_global_kernel(const float* __restrict__ A, float* __restrict__ L, float* __
 // ------------------------------------------------------------------------------------------------
 // host-side dispatch
 // ------------------------------------------------------------------------------------------------
-template <int N, int VARIANT>
-static cudaError_t launch_tpm(const float* A, float* L, long batch, cudaStream_t st) {
-    constexpr int WARPS = (N == 16) ? 6 : 8;
+// HLSD_CHOL16 (environment, read once) selects the N=16 kernel for A/B measurements:
+//   "tpm" one thread per matrix (6 warps/SM), "r2" (default) / "r4": 2 / 4 lanes per matrix.
+static int chol16_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("HLSD_CHOL16");
+        mode = !e ? 2 : (e[0] == 't' ? 1 : (e[1] == '4' ? 4 : 2));
+    }
+    return mode;
+}
+
+template <int N, int VARIANT, int WARPS>
+static cudaError_t launch_tpm_w(const float* A, float* L, long batch, cudaStream_t st) {
     using Cfg = TpmCfg<N>;
     const size_t smem = (size_t)WARPS * Cfg::kSlabFloats * 4 + WARPS * sizeof(uint64_t);
     auto kern = chol_tpm_kernel<N, VARIANT, WARPS>;
@@ -281,6 +423,34 @@ static cudaError_t launch_tpm(const float* A, float* L, long batch, cudaStream_t
     kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(A, L, batch);
     count_launch();
     return cudaGetLastError();
+}
+
+template <int N, int R, int VARIANT, int WARPS>
+static cudaError_t launch_rows(const float* A, float* L, long batch, cudaStream_t st) {
+    using Cfg = TpmCfg<N>;
+    constexpr int MPW = 32 / R;
+    const size_t smem = (size_t)WARPS * MPW * Cfg::kSlot * 4 + WARPS * sizeof(uint64_t);
+    auto kern = chol_rows_kernel<N, R, VARIANT, WARPS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long num_slabs = (batch + MPW - 1) / MPW;
+    long grid = std::min<long>((num_slabs + WARPS - 1) / WARPS, (long)sm_count());
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(A, L, batch);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int N, int VARIANT>
+static cudaError_t launch_tpm(const float* A, float* L, long batch, cudaStream_t st) {
+    if constexpr (N == 16) {
+        switch (chol16_mode()) {
+            case 1: return launch_tpm_w<N, VARIANT, 6>(A, L, batch, st);
+            case 4: return launch_rows<N, 4, VARIANT, 24>(A, L, batch, st);
+            default: return launch_rows<N, 2, VARIANT, 12>(A, L, batch, st);
+        }
+    } else {
+        return launch_tpm_w<N, VARIANT, 8>(A, L, batch, st);
+    }
 }
 
 template <int G, int VARIANT>

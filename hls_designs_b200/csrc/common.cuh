@@ -3,7 +3,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace hlsd {
+
+// compile-time loop: f(std::integral_constant<int, I>) for I in [Begin, End); every index inside the
+// body is a constant expression, so register arrays indexed by it never fall back to local memory
+template <int Begin, int End, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (Begin < End) {
+        f(std::integral_constant<int, Begin>{});
+        static_for<Begin + 1, End>(f);
+    }
+}
 
 // ----------------------------------------------------------------------------------------------
 // Exact arithmetic.  The reference's C-simulation rounds every float operation separately
