@@ -201,6 +201,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (exploration runs only)")
     args = ap.parse_args()
 
     kind, rows, cols, batch, design = WORKLOADS[args.workload]
@@ -304,66 +305,68 @@ def main():
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "gflops": flops(kind, rows, cols) * batch / (med_ms * 1e-3) / 1e9}
 
-    # ---- end to end through the host-pointer C entry point, pinned host buffers ----
-    def pinned(nbytes, dtype, shape):
-        p = lib.hlsd_host_alloc(nbytes)
-        if not p:
-            raise MemoryError(lib.hlsd_last_error().decode())
-        arr = np.ctypeslib.as_array((ctypes.c_byte * nbytes).from_address(p)).view(dtype).reshape(shape)
-        return p, arr
+    e2e = None
+    if not args.no_e2e:
+        # ---- end to end through the host-pointer C entry point, pinned host buffers ----
+        def pinned(nbytes, dtype, shape):
+            p = lib.hlsd_host_alloc(nbytes)
+            if not p:
+                raise MemoryError(lib.hlsd_last_error().decode())
+            arr = np.ctypeslib.as_array((ctypes.c_byte * nbytes).from_address(p)).view(dtype).reshape(shape)
+            return p, arr
 
-    e2e_batch = batch
-    in_bytes = e2e_batch * rows * cols * 4
-    pA, hA = pinned(in_bytes, np.float32, (e2e_batch, rows, cols))
-    hA[...] = A.cpu().numpy()
-    outs, ptrs = [], [pA]
-    if kind == "chol":
-        shapes = [((e2e_batch, rows, rows), np.float32)]
-    elif kind == "lu":
-        shapes = [((e2e_batch, rows, rows), np.float32), ((e2e_batch, rows, rows), np.float32), ((e2e_batch, rows), np.int32)]
-    else:
-        shapes = [((e2e_batch, rows, rows), np.float32), ((e2e_batch, rows, cols), np.float32)]
-    out_bytes = 0
-    for shp, dt in shapes:
-        nb = int(np.prod(shp)) * 4
-        p, arr = pinned(nb, dt, shp)
-        ptrs.append(p)
-        outs.append(arr)
-        out_bytes += nb
-    dcode = {**hd.CHOL_DESIGNS, **hd.LU_DESIGNS, **hd.QR_DESIGNS}[design]
-    pcode = hd.PATHS[args.path]
-
-    def host_step():
+        e2e_batch = batch
+        in_bytes = e2e_batch * rows * cols * 4
+        pA, hA = pinned(in_bytes, np.float32, (e2e_batch, rows, cols))
+        hA[...] = A.cpu().numpy()
+        outs, ptrs = [], [pA]
         if kind == "chol":
-            rc = lib.hlsd_cholesky_host(hA.ctypes.data, outs[0].ctypes.data, rows, e2e_batch, dcode, pcode)
+            shapes = [((e2e_batch, rows, rows), np.float32)]
         elif kind == "lu":
-            rc = lib.hlsd_lu_host(hA.ctypes.data, outs[0].ctypes.data, outs[1].ctypes.data, outs[2].ctypes.data, rows,
-                                  e2e_batch, dcode, pcode)
+            shapes = [((e2e_batch, rows, rows), np.float32), ((e2e_batch, rows, rows), np.float32), ((e2e_batch, rows), np.int32)]
         else:
-            rc = lib.hlsd_qr_host(hA.ctypes.data, outs[0].ctypes.data, outs[1].ctypes.data, rows, cols, e2e_batch, dcode, pcode)
-        if rc:
-            raise RuntimeError(lib.hlsd_last_error().decode())
+            shapes = [((e2e_batch, rows, rows), np.float32), ((e2e_batch, rows, cols), np.float32)]
+        out_bytes = 0
+        for shp, dt in shapes:
+            nb = int(np.prod(shp)) * 4
+            p, arr = pinned(nb, dt, shp)
+            ptrs.append(p)
+            outs.append(arr)
+            out_bytes += nb
+        dcode = {**hd.CHOL_DESIGNS, **hd.LU_DESIGNS, **hd.QR_DESIGNS}[design]
+        pcode = hd.PATHS[args.path]
 
-    host_step()  # warm-up (stream/buffer creation paths, page faults)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.region(True)
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        host_step()  # returns when the outputs are complete in host memory
-    e2e_s = time.perf_counter() - t0
-    sampler.region(False)
-    e2e_units, e2e_ms = combine_ranks(e2e_batch * args.e2e_steps, e2e_s * 1e3, dev)
-    e2e = {"value": e2e_units / (e2e_ms * 1e-3), "unit": METRIC, "h2d_bytes_per_step": in_bytes,
-           "d2h_bytes_per_step": out_bytes, "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps,
-           "api": f"hlsd_{'cholesky' if kind == 'chol' else kind}_host (C ABI, pinned host buffers, chunked 3-stream pipeline)"}
-    # the e2e result must be the same answer the resident leg produced
-    ref_out = out[0] if isinstance(out, tuple) else out
-    first = outs[0][:256]
-    e2e["matches_resident"] = bool(np.array_equal(first, ref_out[:256].cpu().numpy()))
-    for p in ptrs:
-        lib.hlsd_host_free(p)
+        def host_step():
+            if kind == "chol":
+                rc = lib.hlsd_cholesky_host(hA.ctypes.data, outs[0].ctypes.data, rows, e2e_batch, dcode, pcode)
+            elif kind == "lu":
+                rc = lib.hlsd_lu_host(hA.ctypes.data, outs[0].ctypes.data, outs[1].ctypes.data, outs[2].ctypes.data, rows,
+                                      e2e_batch, dcode, pcode)
+            else:
+                rc = lib.hlsd_qr_host(hA.ctypes.data, outs[0].ctypes.data, outs[1].ctypes.data, rows, cols, e2e_batch, dcode, pcode)
+            if rc:
+                raise RuntimeError(lib.hlsd_last_error().decode())
+
+        host_step()  # warm-up (stream/buffer creation paths, page faults)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler.region(True)
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            host_step()  # returns when the outputs are complete in host memory
+        e2e_s = time.perf_counter() - t0
+        sampler.region(False)
+        e2e_units, e2e_ms = combine_ranks(e2e_batch * args.e2e_steps, e2e_s * 1e3, dev)
+        e2e = {"value": e2e_units / (e2e_ms * 1e-3), "unit": METRIC, "h2d_bytes_per_step": in_bytes,
+               "d2h_bytes_per_step": out_bytes, "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps,
+               "api": f"hlsd_{'cholesky' if kind == 'chol' else kind}_host (C ABI, pinned host buffers, chunked 3-stream pipeline)"}
+        # the e2e result must be the same answer the resident leg produced
+        ref_out = out[0] if isinstance(out, tuple) else out
+        first = outs[0][:256]
+        e2e["matches_resident"] = bool(np.array_equal(first, ref_out[:256].cpu().numpy()))
+        for p in ptrs:
+            lib.hlsd_host_free(p)
 
     clocks = sampler.summary()
     cpu = None

@@ -21,6 +21,7 @@ SIGNATURES = {
     "hlsd_qr_dev": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i, _i, _vp]),
     "hlsd_host_alloc": (_vp, [ctypes.c_size_t]),
     "hlsd_host_free": (None, [_vp]),
+    "hlsd_release_workspace": (None, []),
     "hlsd_set_device": (_i, [_i]),
     "hlsd_device_count": (_i, []),
     "hlsd_launch_count": (_i64, []),

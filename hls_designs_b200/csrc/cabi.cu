@@ -75,10 +75,14 @@ static int chol_dev(const float* A, float* L, int n, int64_t batch, int design, 
     if (n < 1 || batch < 0) return fail(HLSD_ERR_INVALID, "n must be >= 1 and batch >= 0");
     if (!chol_variant(design, &variant)) return fail(HLSD_ERR_INVALID, "unknown Cholesky design");
     if (int rc = check_path(flags, &path)) return rc;
+    // large right-looking problems go to the blocked tensor-core path unless a path was forced
+    if (path == HLSD_PATH_AUTO && variant == 0 && n >= 256 && n % 128 == 0 && batch <= 65535 &&
+        (((uintptr_t)A | (uintptr_t)L) & 15) == 0)
+        path = HLSD_PATH_TENSOR;
     if (path == HLSD_PATH_BLOCKED || path == HLSD_PATH_TENSOR) {
         if (variant != 0) return fail(HLSD_ERR_UNSUPPORTED, "blocked Cholesky implements the right-looking designs only");
         cudaError_t e = cholesky_blocked(A, L, n, (long)batch, path == HLSD_PATH_TENSOR, st);
-        if (e == cudaErrorNotSupported) return fail(HLSD_ERR_UNSUPPORTED, "blocked Cholesky needs n to be a multiple of 64, n >= 128");
+        if (e == cudaErrorNotSupported) return fail(HLSD_ERR_UNSUPPORTED, "the blocked tensor-core Cholesky needs n % 128 == 0, n >= 256, batch <= 65535 (HLSD_PATH_BLOCKED, the SIMT trailing update, is not built yet)");
         if (e != cudaSuccess) return cuda_fail(e, "cholesky_blocked");
         return 0;
     }
@@ -128,67 +132,97 @@ struct Buf {
     size_t bytes_per_matrix;
 };
 
+// Per-thread, per-device staging workspace kept across calls: three streams and, per stream, one
+// growable device buffer per argument.  (cudaMalloc / cudaFree / stream creation per call cost more
+// than the whole factorisation of a small batch.)  Released by hlsd_release_workspace().
+struct Workspace {
+    static constexpr int kStreams = 3;
+    int device = -1;
+    cudaStream_t st[kStreams] = {};
+    std::vector<void*> buf[kStreams];
+    std::vector<size_t> cap[kStreams];
+
+    void release() {
+        for (int i = 0; i < kStreams; i++) {
+            for (void* p : buf[i]) cudaFree(p);
+            buf[i].clear();
+            cap[i].clear();
+            if (st[i]) cudaStreamDestroy(st[i]);
+            st[i] = nullptr;
+        }
+        device = -1;
+    }
+    cudaError_t prepare(int slot, const std::vector<size_t>& bytes) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev != device) {
+            release();
+            device = dev;
+        }
+        if (!st[slot] && (e = cudaStreamCreateWithFlags(&st[slot], cudaStreamNonBlocking)) != cudaSuccess) return e;
+        buf[slot].resize(bytes.size(), nullptr);
+        cap[slot].resize(bytes.size(), 0);
+        for (size_t i = 0; i < bytes.size(); i++)
+            if (cap[slot][i] < bytes[i]) {
+                if (buf[slot][i]) cudaFree(buf[slot][i]);
+                buf[slot][i] = nullptr;
+                cap[slot][i] = 0;
+                if ((e = cudaMalloc(&buf[slot][i], bytes[i])) != cudaSuccess) return e;
+                cap[slot][i] = bytes[i];
+            }
+        return cudaSuccess;
+    }
+    ~Workspace() {}  // the CUDA context may already be gone at thread exit: leak rather than crash
+};
+static thread_local Workspace g_ws;
+
 template <typename LaunchF>
 static int run_host_pipeline(int64_t batch, std::vector<Buf> bufs, LaunchF launch) {
     if (batch == 0) return 0;
     size_t per_matrix = 0;
     for (auto& b : bufs) per_matrix += b.bytes_per_matrix;
-    const size_t kChunkBytes = (size_t)96 << 20;
+    const size_t kChunkBytes = (size_t)64 << 20;
     int64_t chunk = (int64_t)(kChunkBytes / (per_matrix ? per_matrix : 1));
     if (chunk < 1) chunk = 1;
     if (chunk > batch) chunk = batch;
     chunk = (chunk + 31) / 32 * 32;  // keep chunk starts 16-byte aligned for every element size used here
-    const int kStreams = 3;
-    cudaStream_t st[kStreams] = {};
-    std::vector<void*> dev[kStreams];
     int rc = 0;
     cudaError_t e = cudaSuccess;
-    int made = 0;
-    for (; made < kStreams && made * chunk < batch; made++) {
-        if ((e = cudaStreamCreateWithFlags(&st[made], cudaStreamNonBlocking)) != cudaSuccess) {
-            rc = cuda_fail(e, "cudaStreamCreate");
+    int used = 0;
+    std::vector<size_t> bytes;
+    for (auto& b : bufs) bytes.push_back(b.bytes_per_matrix * (size_t)chunk);
+    for (; used < Workspace::kStreams && used * chunk < batch; used++)
+        if ((e = g_ws.prepare(used, bytes)) != cudaSuccess) {
+            rc = cuda_fail(e, "staging workspace");
             break;
         }
-        for (auto& b : bufs) {
-            void* p = nullptr;
-            if ((e = cudaMalloc(&p, b.bytes_per_matrix * (size_t)chunk)) != cudaSuccess) {
-                rc = cuda_fail(e, "cudaMalloc");
-                break;
-            }
-            dev[made].push_back(p);
-        }
-        if (rc) {
-            made++;
-            break;
-        }
-    }
     if (!rc) {
         int slot = 0;
-        for (int64_t m0 = 0; m0 < batch && !rc; m0 += chunk, slot = (slot + 1) % made) {
+        for (int64_t m0 = 0; m0 < batch && !rc; m0 += chunk, slot = (slot + 1) % used) {
             const int64_t cnt = (batch - m0 < chunk) ? batch - m0 : chunk;
+            cudaStream_t st = g_ws.st[slot];
+            std::vector<void*>& dev = g_ws.buf[slot];
             for (size_t i = 0; i < bufs.size() && !rc; i++)
                 if (bufs[i].host_in) {
-                    e = cudaMemcpyAsync(dev[slot][i], (const char*)bufs[i].host_in + bufs[i].bytes_per_matrix * (size_t)m0,
-                                        bufs[i].bytes_per_matrix * (size_t)cnt, cudaMemcpyHostToDevice, st[slot]);
+                    e = cudaMemcpyAsync(dev[i], (const char*)bufs[i].host_in + bufs[i].bytes_per_matrix * (size_t)m0,
+                                        bufs[i].bytes_per_matrix * (size_t)cnt, cudaMemcpyHostToDevice, st);
                     if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync H2D");
                 }
-            if (!rc) rc = launch(dev[slot], cnt, st[slot]);
+            if (!rc) rc = launch(dev, cnt, st);
             for (size_t i = 0; i < bufs.size() && !rc; i++)
                 if (bufs[i].host_out) {
-                    e = cudaMemcpyAsync((char*)bufs[i].host_out + bufs[i].bytes_per_matrix * (size_t)m0, dev[slot][i],
-                                        bufs[i].bytes_per_matrix * (size_t)cnt, cudaMemcpyDeviceToHost, st[slot]);
+                    e = cudaMemcpyAsync((char*)bufs[i].host_out + bufs[i].bytes_per_matrix * (size_t)m0, dev[i],
+                                        bufs[i].bytes_per_matrix * (size_t)cnt, cudaMemcpyDeviceToHost, st);
                     if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
                 }
         }
     }
-    for (int i = 0; i < made; i++) {
-        if (st[i]) {
-            e = cudaStreamSynchronize(st[i]);
+    for (int i = 0; i < used; i++)
+        if (g_ws.st[i]) {
+            e = cudaStreamSynchronize(g_ws.st[i]);
             if (e != cudaSuccess && !rc) rc = cuda_fail(e, "cudaStreamSynchronize");
         }
-        for (void* p : dev[i]) cudaFree(p);
-        if (st[i]) cudaStreamDestroy(st[i]);
-    }
     return rc;
 }
 
@@ -254,6 +288,8 @@ void* hlsd_host_alloc(size_t bytes) {
 void hlsd_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
+
+void hlsd_release_workspace(void) { g_ws.release(); }
 
 int hlsd_set_device(int device) {
     cudaError_t e = cudaSetDevice(device);

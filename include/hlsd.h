@@ -86,6 +86,9 @@ int hlsd_qr_dev(const float* dA, float* dQ, float* dR, int rows, int cols, int64
 /* ---- pinned host buffers for the *_host entry points (optional; pageable memory also works) ---- */
 void* hlsd_host_alloc(size_t bytes);
 void hlsd_host_free(void* p);
+/* The *_host entry points keep their device staging buffers and streams (per calling thread) between
+ * calls; this frees them. */
+void hlsd_release_workspace(void);
 
 /* ---- housekeeping ---- */
 int hlsd_set_device(int device);           /* cudaSetDevice for the calling thread */
