@@ -448,6 +448,10 @@ static cudaError_t launch_tpm(const float* A, float* L, long batch, cudaStream_t
             case 4: return launch_rows<N, 4, VARIANT, 24>(A, L, batch, st);
             default: return launch_rows<N, 2, VARIANT, 12>(A, L, batch, st);
         }
+    } else if constexpr (N == 32) {
+        return launch_rows<N, 16, VARIANT, 12>(A, L, batch, st);
+    } else if constexpr (N == 64) {
+        return launch_rows<N, 32, VARIANT, 12>(A, L, batch, st);
     } else {
         return launch_tpm_w<N, VARIANT, 8>(A, L, batch, st);
     }
@@ -475,6 +479,8 @@ static cudaError_t chol_dispatch(const float* A, float* L, int n, long batch, in
         if (aligned && n == 4) return launch_tpm<4, VARIANT>(A, L, batch, st);
         if (aligned && n == 8) return launch_tpm<8, VARIANT>(A, L, batch, st);
         if (aligned && n == 16) return launch_tpm<16, VARIANT>(A, L, batch, st);
+        if (aligned && n == 32) return launch_tpm<32, VARIANT>(A, L, batch, st);
+        if (aligned && n == 64) return launch_tpm<64, VARIANT>(A, L, batch, st);
         if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
     }
     const size_t per = ((size_t)n * (n | 1) + n) * 4;

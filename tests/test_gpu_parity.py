@@ -19,7 +19,7 @@ QR_DESIGNS = ("qr_v1.1", "qr_v1.2", "qr_v2.1")
 
 def _paths_for(n, kind):
     paths = ["auto", "group", "global"]
-    if (kind == "chol" and n in (4, 8, 16)) or (kind in ("lu", "qr") and n in (4, 8)):
+    if (kind == "chol" and n in (4, 8, 16, 32, 64)) or (kind == "lu" and n in (4, 8, 16, 32, 64)) or (kind == "qr" and n in (4, 8)):
         paths.append("tpm")
     return paths
 
@@ -147,7 +147,7 @@ def test_edge_cases():
     got, want = hd.lu(B), restate.lu(B)
     assert np.array_equal(got[2], want[2])
     with pytest.raises(hd.HlsdError):
-        hd.cholesky(gen_spd(32), path="tpm")  # forced path that cannot serve the size
+        hd.cholesky(gen_spd(48), path="tpm")  # forced path that cannot serve the size
     with pytest.raises(hd.HlsdError):
         hd.qr(np.ones((3, 5), np.float32))
 
