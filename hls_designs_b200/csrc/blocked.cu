@@ -7,12 +7,13 @@
 // below the diagonal block).  That part runs on the tcgen05 tensor cores; everything that is not a
 // dense contraction stays on CUDA cores:
 //
-//   per panel p (columns o = 128 p .. o+127), all matrices of the batch at once:
+//   per panel p (columns o = 128 p .. o+127), all matrices of the batch at once (panel 0 reads its
+//   inputs straight from A, so the operand is never copied):
 //     1. blk_diag_kernel   (SIMT, register-tiled)          L11 = chol(A11), W = inv(L11)
 //     2. blk_mma_kernel<TRSM>  (tcgen05)  L21 = A21 * W^T        (rows below the diagonal block)
 //     3. blk_mma_kernel<SYRK>  (tcgen05)  A22 -= L21 * L21^T     (lower block triangle only)
 //
-// Tensor-core arithmetic: fp32 operands are split on the fly into tf32 hi + tf32 lo parts and each
+// Tensor-core arithmetic: fp32 operands are split on the fly into tf32 hi (truncation) + tf32 lo parts and each
 // product is formed as a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (3xTF32) with fp32 accumulation in TMEM,
 // which keeps ~21 mantissa bits (a single tf32 pass keeps 10).  The result is not bit-identical to
 // the csim (different summation order, split products) but agrees to fp32 round-off level; the
@@ -20,10 +21,11 @@
 //
 // blk_mma_kernel: one CTA = one 128x128 output tile, D = A * B^T with A = 128 rows x 128 k,
 // B = 128 rows x 128 k, both K-major fp32 in global memory.  K is consumed in four chunks of 32:
-// 256 threads load the chunk with coalesced 16-byte loads, split hi/lo in registers and store the
-// four operand tiles (64 KB together, so three CTAs share an SM and overlap each other's load, MMA
-// and epilogue phases) into shared memory in the canonical K-major SWIZZLE_128B layout (the layout
-// TMA would produce; TMA itself cannot split, so the staging is done by the threads); one elected
+// cp.async (LDGSTS) copies the raw fp32 chunk of A and B straight into shared memory in the
+// canonical K-major SWIZZLE_128B layout, double-buffered so that chunk c+1 streams in while chunk
+// c is being multiplied; the raw tile itself is the tf32 "hi" operand (the tensor core reads the
+// upper 19 bits of each word) and the threads only add the "lo" tile (x - hi, rounded to tf32);
+// 96 KB per CTA, two CTAs per SM overlap each other's MMA and epilogue phases; one elected
 // thread issues 12 tcgen05.mma.kind::tf32 (M128 N128 K8) per chunk; completion is tracked with
 // tcgen05.commit on an mbarrier; the epilogue reads the accumulator with tcgen05.ld (32x32b.x32)
 // and either stores it (TRSM) or subtracts it from C in place (SYRK).
@@ -103,22 +105,22 @@ __device__ __forceinline__ float to_tf32(float x) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// L = tril(A): the factorisation runs in place in L
+// Zero the blocks strictly above the block diagonal of L (nothing else ever writes them).  The
+// operand A itself is never copied: panel 0 reads its inputs from A and writes to L, later panels
+// work in place in L.  grid: (upper blocks, batch)
 // ------------------------------------------------------------------------------------------------
-__global__ void blk_init_kernel(const float* __restrict__ A, float* __restrict__ L, int n, long total4) {
-    const long stride = (long)gridDim.x * blockDim.x;
+__global__ void __launch_bounds__(256)
+blk_zero_upper_kernel(float* __restrict__ L, int n) {
+    int r = blockIdx.x;  // unrank into (bi < bj)
+    int bj = (int)((sqrtf(8.0f * r + 1.0f) + 1.0f) * 0.5f);
+    while (bj * (bj - 1) / 2 > r) bj--;
+    while ((bj + 1) * bj / 2 <= r) bj++;
+    const int bi = r - bj * (bj - 1) / 2;
+    float4* base = reinterpret_cast<float4*>(L + (long)blockIdx.y * n * n + (long)bi * NB * n + bj * NB);
     const int n4 = n / 4;
-    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total4; e += stride) {
-        const long rowid = e / n4;
-        const int c4 = (int)(e - rowid * n4);
-        const int i = (int)(rowid % n);
-        float4 v = reinterpret_cast<const float4*>(A)[e];
-        const int j = 4 * c4;
-        if (j + 0 > i) v.x = 0.0f;
-        if (j + 1 > i) v.y = 0.0f;
-        if (j + 2 > i) v.z = 0.0f;
-        if (j + 3 > i) v.w = 0.0f;
-        reinterpret_cast<float4*>(L)[e] = v;
+    for (int e = threadIdx.x; e < NB * (NB / 4); e += 256) {
+        const int row = e / (NB / 4), c4 = e % (NB / 4);
+        base[(long)row * n4 + c4] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
 
@@ -136,19 +138,20 @@ __global__ void blk_init_kernel(const float* __restrict__ A, float* __restrict__
 // owners of row k of W scale and publish it; everyone applies the update; the owner of (k+1, k+1)
 // takes the next square root.  Plain fp32 FMA arithmetic (tensor path: tolerance-checked).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 1)
-blk_diag_kernel(float* __restrict__ L, float* __restrict__ W, int n, int o) {
+__global__ void __launch_bounds__(512, 2)
+blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __restrict__ W, int n, int o) {
     __shared__ float ubuf[NB];
     __shared__ float sdiag;
     const int tr = threadIdx.x >> 5, tc = threadIdx.x & 31;
     float* blk = L + (long)blockIdx.x * n * n + (long)o * n + o;
+    const float* sblk = S + (long)blockIdx.x * n * n + (long)o * n + o;  // S = A for panel 0, L afterwards
     float v[8][4];
 #pragma unroll
     for (int ia = 0; ia < 8; ia++)
 #pragma unroll
         for (int ib = 0; ib < 4; ib++) {
             const int i = tr + 16 * ia, j = tc + 32 * ib;
-            v[ia][ib] = (j <= i) ? blk[(long)i * n + j] : 0.0f;
+            v[ia][ib] = (j <= i) ? sblk[(long)i * n + j] : 0.0f;
         }
     if (threadIdx.x == 0) sdiag = sqrtf(v[0][0]);
     __syncthreads();
@@ -227,36 +230,51 @@ blk_diag_kernel(float* __restrict__ L, float* __restrict__ W, int n, int o) {
 enum { MMA_TRSM = 0, MMA_SYRK = 1 };
 
 struct MmaSmem {
-    // four operand tiles, each 128 rows x 32 k fp32 = one swizzle atom of [128 rows][128 B]
+    // per 32-wide K chunk an operand tile is 128 rows x 32 k fp32 = one swizzle atom [128 rows][128 B].
+    // raw fp32 tiles (2 stages x {A, B}) are filled by cp.async and double as the tf32 "hi" operands:
+    // the tensor core reads only the upper 19 bits of each 32-bit container, i.e. hi = trunc_tf32(x);
+    // the "lo" tiles hold rna_tf32(x - hi) computed by the threads.
     static constexpr int kChunkK = 32;
     static constexpr int kTileBytes = 128 * kChunkK * 4;
-    static constexpr int kAhi = 0, kAlo = kTileBytes, kBhi = 2 * kTileBytes, kBlo = 3 * kTileBytes;
-    static constexpr int kBar = 4 * kTileBytes;
+    static constexpr int kStages = 1;  // raw stages: 1 -> 64 KB per CTA (3 CTAs/SM), 2 -> 96 KB (2 CTAs/SM)
+    static constexpr int kRawA = 0, kRawB = kStages * kTileBytes;      // [stage] each
+    static constexpr int kLoA = 2 * kStages * kTileBytes, kLoB = kLoA + kTileBytes;
+    static constexpr int kBar = kLoB + kTileBytes;
     static constexpr int kTmemPtr = kBar + 8;
     static constexpr int kTotal = kBar + 16 + 1024;  // + slack for the 1024-byte alignment of the tiles
 };
 
-__device__ __forceinline__ void split_store(unsigned char* hi_tile, unsigned char* lo_tile, int row, int c4, float4 v) {
-    // 16-byte chunk c4 (4 k) of `row` inside a 128 x 32 tile; SWIZZLE_128B: chunk index ^= row % 8
-    const int off = row * 128 + ((c4 ^ (row & 7)) << 4);
-    float4 h, l;
-    h.x = to_tf32(v.x), h.y = to_tf32(v.y), h.z = to_tf32(v.z), h.w = to_tf32(v.w);
-    l.x = to_tf32(v.x - h.x), l.y = to_tf32(v.y - h.y), l.z = to_tf32(v.z - h.z), l.w = to_tf32(v.w - h.w);
-    *reinterpret_cast<float4*>(hi_tile + off) = h;
-    *reinterpret_cast<float4*>(lo_tile + off) = l;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// lo part of a float4 sitting in a raw tile: x - trunc_tf32(x), rounded to tf32
+__device__ __forceinline__ float4 lo_of(float4 v) {
+    float4 l;
+    l.x = to_tf32(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
+    l.y = to_tf32(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
+    l.z = to_tf32(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
+    l.w = to_tf32(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+    return l;
 }
 
 // grid: (tiles, batch).  TRSM: tile t = row block t of the panel below the diagonal block.
 //                         SYRK: tile t -> (tj >= ti) in the lower block triangle of the trailing matrix.
 template <int MODE>
-__global__ void __launch_bounds__(256, 2)
-blk_mma_kernel(float* __restrict__ L, const float* __restrict__ W, int n, int o) {
+__global__ void __launch_bounds__(256, MmaSmem::kStages == 1 ? 3 : 2)
+blk_mma_kernel(const float* __restrict__ S, float* __restrict__ L, const float* __restrict__ W, int n, int o) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + MmaSmem::kBar);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + MmaSmem::kTmemPtr);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     float* Lb = L + (long)blockIdx.y * n * n;
+    const float* Sb = S + (long)blockIdx.y * n * n;  // S = A for panel 0 (inputs not yet in L), L afterwards
 
     int tj, ti;
     if constexpr (MODE == MMA_TRSM) {
@@ -272,7 +290,8 @@ blk_mma_kernel(float* __restrict__ L, const float* __restrict__ W, int n, int o)
     }
     const int row0 = o + NB;  // first row of the panel below the diagonal block / of the trailing matrix
     // operand rows (K-major, k = panel columns o .. o+127)
-    const float* Arows = Lb + (long)(row0 + tj * NB) * n + o;
+    // TRSM multiplies the not yet factored panel rows (from S); SYRK multiplies finished L21 rows (from L)
+    const float* Arows = (MODE == MMA_TRSM ? Sb : Lb) + (long)(row0 + tj * NB) * n + o;
     const long lda = n;
     const float* Brows;
     long ldb;
@@ -295,36 +314,50 @@ blk_mma_kernel(float* __restrict__ L, const float* __restrict__ W, int n, int o)
     tc_fence_after();
     const uint32_t tmem_d = *tmem_ptr;
 
-    unsigned char* sAhi = smem + MmaSmem::kAhi;
-    unsigned char* sAlo = smem + MmaSmem::kAlo;
-    unsigned char* sBhi = same ? sAhi : smem + MmaSmem::kBhi;
-    unsigned char* sBlo = same ? sAlo : smem + MmaSmem::kBlo;
-
     constexpr int kChunks = NB / MmaSmem::kChunkK;  // 4 chunks of 32 k
-    float4 ra[4], rb[4];
-    auto gload = [&](int chunk) {
-#pragma unroll
-        for (int it = 0; it < 4; it++) {
-            const int idx = it * 256 + t, row = idx >> 3, c4 = idx & 7;
-            ra[it] = *reinterpret_cast<const float4*>(Arows + row * lda + chunk * MmaSmem::kChunkK + c4 * 4);
-            if (!same) rb[it] = *reinterpret_cast<const float4*>(Brows + row * ldb + chunk * MmaSmem::kChunkK + c4 * 4);
-        }
+    // 16-byte piece `it` of this thread: row = idx / 8, chunk-of-16-bytes c4 = idx % 8 (SWIZZLE_128B: c4 ^= row % 8)
+    auto piece_off = [&](int it) {
+        const int idx = it * 256 + t, row = idx >> 3, c4 = idx & 7;
+        return row * 128 + ((c4 ^ (row & 7)) << 4);
     };
-    gload(0);
-    for (int chunk = 0; chunk < kChunks; chunk++) {
+    auto issue_loads = [&](int chunk) {
+        unsigned char* ra = smem + MmaSmem::kRawA + (chunk % MmaSmem::kStages) * MmaSmem::kTileBytes;
+        unsigned char* rb = smem + MmaSmem::kRawB + (chunk % MmaSmem::kStages) * MmaSmem::kTileBytes;
 #pragma unroll
         for (int it = 0; it < 4; it++) {
             const int idx = it * 256 + t, row = idx >> 3, c4 = idx & 7;
-            split_store(sAhi, sAlo, row, c4, ra[it]);
-            if (!same) split_store(sBhi, sBlo, row, c4, rb[it]);
+            cp_async16(ra + piece_off(it), Arows + row * lda + chunk * MmaSmem::kChunkK + c4 * 4);
+            if (!same) cp_async16(rb + piece_off(it), Brows + row * ldb + chunk * MmaSmem::kChunkK + c4 * 4);
         }
-        fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        cp_async_commit();
+    };
+    issue_loads(0);
+    for (int chunk = 0; chunk < kChunks; chunk++) {
+        unsigned char* ra = smem + MmaSmem::kRawA + (chunk % MmaSmem::kStages) * MmaSmem::kTileBytes;
+        unsigned char* rb = same ? ra : smem + MmaSmem::kRawB + (chunk % MmaSmem::kStages) * MmaSmem::kTileBytes;
+        unsigned char* la = smem + MmaSmem::kLoA;
+        unsigned char* lb = same ? la : smem + MmaSmem::kLoB;
+        // the other raw stage was last read by the MMAs of chunk-1, which have completed (mbar_wait below)
+        if (MmaSmem::kStages == 2 && chunk + 1 < kChunks) {
+            issue_loads(chunk + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        // each thread splits exactly the pieces it copied itself, so no barrier is needed before reading them
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int off = piece_off(it);
+            *reinterpret_cast<float4*>(la + off) = lo_of(*reinterpret_cast<const float4*>(ra + off));
+            if (!same) *reinterpret_cast<float4*>(lb + off) = lo_of(*reinterpret_cast<const float4*>(rb + off));
+        }
+        fence_async_smem();  // cp.async / st.shared data -> visible to the tensor core's async-proxy reads
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
         if (t == 0) {
-            const uint64_t dAhi = make_sw128_desc(smem_u32(sAhi)), dAlo = make_sw128_desc(smem_u32(sAlo));
-            const uint64_t dBhi = make_sw128_desc(smem_u32(sBhi)), dBlo = make_sw128_desc(smem_u32(sBlo));
+            const uint64_t dAhi = make_sw128_desc(smem_u32(ra)), dAlo = make_sw128_desc(smem_u32(la));
+            const uint64_t dBhi = make_sw128_desc(smem_u32(rb)), dBlo = make_sw128_desc(smem_u32(lb));
 #pragma unroll
             for (int kk = 0; kk < MmaSmem::kChunkK / 8; kk++) {
                 // k-step kk: 8 tf32 = 32 bytes further inside the 128-byte swizzled row
@@ -336,33 +369,49 @@ blk_mma_kernel(float* __restrict__ L, const float* __restrict__ W, int n, int o)
             }
             umma_commit(bar);
         }
-        if (chunk + 1 < kChunks) gload(chunk + 1);  // next chunk's global loads fly while the tensor core works
-        mbar_wait(bar, (uint32_t)(chunk & 1));  // MMAs done: operand tiles may be overwritten / accumulator is final
+        mbar_wait(bar, (uint32_t)(chunk & 1));  // MMAs done: lo tiles and this raw stage are free again
         tc_fence_after();
+        if (MmaSmem::kStages == 1 && chunk + 1 < kChunks) issue_loads(chunk + 1);
     }
 
-    // epilogue: thread -> accumulator row 32*(warp%4)+lane, 64 columns (warp/4)
-    const int drow = (warp & 3) * 32 + lane;
-    const int dcol0 = (warp >> 2) * 64;
-    float* Crow;
-    if constexpr (MODE == MMA_TRSM) Crow = Lb + (long)(row0 + tj * NB + drow) * n + o;                      // overwrite A21
-    else Crow = Lb + (long)(row0 + tj * NB + drow) * n + (row0 + ti * NB);                                  // C tile
+    // epilogue.  TMEM -> registers (thread = accumulator row 32*(warp%4)+lane, 64 columns (warp/4)) ->
+    // shared memory (the operand tiles are free now; 128 x 128 fp32 = 64 KB, 16-byte pieces XOR-swizzled
+    // by row so that both the row-per-lane writes and the row-per-warp reads are conflict-free) ->
+    // coalesced read-modify-write of C, one 512-byte row per warp instruction.
+    {
+        float* stage = reinterpret_cast<float*>(smem);
+        const int drow = (warp & 3) * 32 + lane;
+        const int dcol0 = (warp >> 2) * 64;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        float acc[32];
-        const int col = dcol0 + h * 32;
-        tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col, acc);
-        float4* c4p = reinterpret_cast<float4*>(Crow + col);
+        for (int h = 0; h < 2; h++) {
+            float acc[32];
+            const int col = dcol0 + h * 32;
+            tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col, acc);
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
+            for (int q = 0; q < 8; q++) {
+                const int c4 = (col >> 2) + q;  // 16-byte piece index inside the row (0..31)
+                *reinterpret_cast<float4*>(stage + drow * 128 + ((c4 ^ (drow & 7)) << 2)) =
+                    make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            }
+        }
+        __syncthreads();
+        float* Cbase;
+        if constexpr (MODE == MMA_TRSM) Cbase = Lb + (long)(row0 + tj * NB) * n + o;       // L21
+        else Cbase = Lb + (long)(row0 + tj * NB) * n + (row0 + ti * NB);                   // C tile
+        const float* Csrc = Sb + (long)(row0 + tj * NB) * n + (row0 + ti * NB);            // SYRK reads C from S
+#pragma unroll 4
+        for (int rr = 0; rr < 16; rr++) {
+            const int row = warp * 16 + rr;
+            const float4 d = *reinterpret_cast<const float4*>(stage + row * 128 + ((lane ^ (row & 7)) << 2));
+            float4* cp = reinterpret_cast<float4*>(Cbase + (long)row * n) + lane;
             float4 v;
             if constexpr (MODE == MMA_TRSM) {
-                v = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                v = d;
             } else {
-                v = c4p[q];
-                v.x -= acc[4 * q], v.y -= acc[4 * q + 1], v.z -= acc[4 * q + 2], v.w -= acc[4 * q + 3];
+                v = *(reinterpret_cast<const float4*>(Csrc + (long)row * n) + lane);
+                v.x -= d.x, v.y -= d.y, v.z -= d.z, v.w -= d.w;
             }
-            c4p[q] = v;
+            *cp = v;
         }
     }
     tc_fence_before();
@@ -381,19 +430,19 @@ cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int us
     if ((e = cudaMallocAsync(&W, sizeof(float) * (size_t)batch * NB * NB, st)) != cudaSuccess) return e;
     cudaFuncSetAttribute(blk_mma_kernel<MMA_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
     cudaFuncSetAttribute(blk_mma_kernel<MMA_SYRK>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
-    const long total4 = batch * (long)n * n / 4;
-    blk_init_kernel<<<(unsigned)std::min<long>((total4 + 255) / 256, (long)sm_count() * 16), 256, 0, st>>>(A, L, n, total4);
-    count_launch();
     const int panels = n / NB;
+    blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, (unsigned)batch), 256, 0, st>>>(L, n);
+    count_launch();
     for (int p = 0; p < panels; p++) {
         const int o = p * NB;
         const int mt = panels - p - 1;  // 128-row blocks below the diagonal block
-        blk_diag_kernel<<<(unsigned)batch, 512, 0, st>>>(L, W, n, o);
+        const float* src = (p == 0) ? A : L;
+        blk_diag_kernel<<<(unsigned)batch, 512, 0, st>>>(src, L, W, n, o);
         count_launch();
         if (mt > 0) {
-            blk_mma_kernel<MMA_TRSM><<<dim3(mt, (unsigned)batch), 256, MmaSmem::kTotal, st>>>(L, W, n, o);
+            blk_mma_kernel<MMA_TRSM><<<dim3(mt, (unsigned)batch), 256, MmaSmem::kTotal, st>>>(src, L, W, n, o);
             count_launch();
-            blk_mma_kernel<MMA_SYRK><<<dim3(mt * (mt + 1) / 2, (unsigned)batch), 256, MmaSmem::kTotal, st>>>(L, W, n, o);
+            blk_mma_kernel<MMA_SYRK><<<dim3(mt * (mt + 1) / 2, (unsigned)batch), 256, MmaSmem::kTotal, st>>>(src, L, W, n, o);
             count_launch();
         }
     }

@@ -147,11 +147,16 @@ __device__ __forceinline__ void qr_factor(float* r, long ldr, float* q, long ldq
                 cs[2 * k + 1] = ss;
             }
             sync();
+            // apply: thread (ty, tx) takes rotations k = ty, ty + GY, ... and elements x = tx, tx + GX, ...
+            // (columns of R to the right of c, then rows of Q); rotations of one step touch disjoint rows
             const int width = cols + rows;
-            for (int k = 0; k < nrot; k++) {
+            constexpr int GX = G > 256 ? 256 : G, GY = G / GX;
+            const int tx = t % GX, ty = t / GX;
+#pragma unroll 2
+            for (int k = ty; k < nrot; k += GY) {
                 const int c = c_lo + k, i = rows - 1 - step + 2 * c;
                 const float cc = cs[2 * k], ss = cs[2 * k + 1];
-                for (int x = t; x < width; x += G) {
+                for (int x = tx; x < width; x += GX) {
                     if (x < cols) {
                         if (x > c) givens_apply(cc, ss, r[(long)(i - 1) * ldr + x], r[(long)i * ldr + x]);
                     } else {
@@ -189,18 +194,22 @@ __device__ __forceinline__ void qr_factor(float* r, long ldr, float* q, long ldq
 }
 
 template <int G, int VARIANT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(G > 256 ? G : 256)
 qr_wave_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restrict__ R, int rows, int cols,
                long batch) {
     extern __shared__ __align__(16) float smem_f[];
-    constexpr int kGroups = 256 / G;
+    constexpr int kBlock = G > 256 ? G : 256;
+    constexpr int kGroups = kBlock / G;
     const int g = threadIdx.x / G, t = threadIdx.x % G;
     const int ldr = cols | 1, ldq = rows | 1;
     const size_t per = (size_t)rows * ldr + (size_t)rows * ldq + 2 * (rows / 2 + 2);
     float* r = smem_f + g * per;
     float* q = r + (size_t)rows * ldr;
     float* cs = q + (size_t)rows * ldq;
-    auto sync = [g]() { group_sync<G>(g); };
+    auto sync = [g]() {
+        if constexpr (G > 256) __syncthreads();
+        else group_sync<G>(g);
+    };
     const long na = (long)rows * cols, nq = (long)rows * rows;
     for (long b = (long)blockIdx.x * kGroups + g; b < batch; b += (long)gridDim.x * kGroups) {
         const float* a = A + b * na;
@@ -274,14 +283,15 @@ static size_t qr_smem_per_matrix(int rows, int cols) {
 
 template <int G, int VARIANT>
 static cudaError_t launch_qr_wave(const float* A, float* Q, float* R, int rows, int cols, long batch, cudaStream_t st) {
-    constexpr int kGroups = 256 / G;
+    constexpr int kBlock = G > 256 ? G : 256;
+    constexpr int kGroups = kBlock / G;
     const size_t smem = qr_smem_per_matrix(rows, cols) * kGroups;
     auto kern = qr_wave_kernel<G, VARIANT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(227 * 1024) / (smem + 1024)));
     long grid = std::min<long>((batch + kGroups - 1) / kGroups, (long)sm_count() * ctas_per_sm);
-    kern<<<(unsigned)grid, 256, smem, st>>>(A, Q, R, rows, cols, batch);
+    kern<<<(unsigned)grid, kBlock, smem, st>>>(A, Q, R, rows, cols, batch);
     count_launch();
     return cudaGetLastError();
 }
@@ -301,6 +311,7 @@ static cudaError_t qr_dispatch(const float* A, float* Q, float* R, int rows, int
         if (per > cap) return cudaErrorInvalidValue;
         if (rows <= 32 && per * 8 <= cap) return launch_qr_wave<32, VARIANT>(A, Q, R, rows, cols, batch, st);
         if (rows <= 64 && per * 2 <= cap) return launch_qr_wave<128, VARIANT>(A, Q, R, rows, cols, batch, st);
+        if (VARIANT == 0 && rows >= 96) return launch_qr_wave<1024, VARIANT>(A, Q, R, rows, cols, batch, st);
         return launch_qr_wave<256, VARIANT>(A, Q, R, rows, cols, batch, st);
     }
     long grid = std::min<long>(batch, (long)sm_count() * 2);
