@@ -451,4 +451,479 @@ cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int us
     return e;
 }
 
+// =================================================================================================
+// Blocked LU with partial pivoting for large N (N a multiple of 128, N <= 1024), batched.
+//
+// Same elimination as the reference's LU designs (LU/lu_v1.1/model4x4/lu.cpp:23-92: pivot = first
+// row with the largest |a_ik|, rows exchanged in columns >= k only, multipliers l_ik = a_ik / a_kk,
+// a_ij -= l_ik u_kj), reorganised right-looking over 128-column panels so that the rank-128
+// trailing update  A22 -= L21 * U12  runs on the tensor cores (3xTF32, as for Cholesky above):
+//
+//   per panel p (columns o .. o+127), all matrices of the batch at once:
+//     1. lu_panel_kernel   (SIMT) pivoted elimination of the (N-o) x 128 panel, thread = row, in four
+//                          32-column sub-panels held in registers; writes L (unit lower) to the L
+//                          buffer, U11 to the working matrix, the pivots to P
+//     2. lu_swap_kernel    (SIMT) the panel's row exchanges applied to the columns right of the panel and,
+//                          LAPACK style, to the L columns left of it (the deferred block updates need L in
+//                          final row order); lu_unswap_kernel converts L back to the reference's convention
+//                          (multipliers stay where they were computed) at the very end
+//     3. lu_inv_kernel     (SIMT) W = inv(L11), unit lower triangular
+//     4. lu_gather_kernel  (SIMT) T0 = A12^T  (k contiguous: the tensor core wants K-major operands)
+//     5. gemm_tile_kernel<0> (tcgen05) T1 = T0 * W^T = U12^T
+//     6. lu_scatter_kernel (SIMT) U12 = T1^T back into the working matrix
+//     7. gemm_tile_kernel<1> (tcgen05) A22 -= L21 * T1^T
+// The working matrix is the U output buffer (a copy of A); what remains in it at the end is U.
+// Not bit-identical to the csim (tensor-core arithmetic; a near-tie between pivot candidates can
+// resolve differently): checked by ||A - P^T L U|| / ||A|| and, where the pivot sequences agree,
+// element-wise.  The exact LU kernels (HLSD_PATH_GLOBAL) stay available at any N.
+// =================================================================================================
+struct TileArgs {
+    const float* A; long lda, strideA;        // A rows of tile row tr: A + b*strideA + (tr*128 + r)*lda + k
+    const float* B; long ldb, strideB;        // B rows of tile col tc: B + b*strideB + (tc*128 + r)*ldb + k
+    const float* Csrc; float* Cdst; long ldc, strideC;  // C tile: + b*strideC + (tr*128 + r)*ldc + tc*128 + c
+    int tiles_col;                            // blockIdx.x -> (tr, tc) = (x / tiles_col, x % tiles_col)
+};
+
+// D = A * B^T over K = 128; SUB ? Cdst = Csrc - D : Cdst = D.  Same pipeline as blk_mma_kernel.
+template <int SUB>
+__global__ void __launch_bounds__(256, MmaSmem::kStages == 1 ? 3 : 2)
+gemm_tile_kernel(TileArgs g) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + MmaSmem::kBar);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + MmaSmem::kTmemPtr);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int tr = blockIdx.x / g.tiles_col, tc = blockIdx.x % g.tiles_col;
+    const long b = blockIdx.y;
+    const float* Arows = g.A + b * g.strideA + (long)tr * NB * g.lda;
+    const float* Brows = g.B + b * g.strideB + (long)tc * NB * g.ldb;
+    if (warp == 0) tmem_alloc(tmem_ptr, 128);
+    if (t == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_ptr;
+    constexpr int kChunks = NB / MmaSmem::kChunkK;
+    auto piece_off = [&](int it) {
+        const int idx = it * 256 + t, row = idx >> 3, c4 = idx & 7;
+        return row * 128 + ((c4 ^ (row & 7)) << 4);
+    };
+    unsigned char* ra = smem + MmaSmem::kRawA;
+    unsigned char* rb = smem + MmaSmem::kRawB;
+    unsigned char* la = smem + MmaSmem::kLoA;
+    unsigned char* lb = smem + MmaSmem::kLoB;
+    auto issue_loads = [&](int chunk) {
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int idx = it * 256 + t, row = idx >> 3, c4 = idx & 7;
+            cp_async16(ra + piece_off(it), Arows + row * g.lda + chunk * MmaSmem::kChunkK + c4 * 4);
+            cp_async16(rb + piece_off(it), Brows + row * g.ldb + chunk * MmaSmem::kChunkK + c4 * 4);
+        }
+        cp_async_commit();
+    };
+    issue_loads(0);
+    for (int chunk = 0; chunk < kChunks; chunk++) {
+        cp_async_wait<0>();
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int off = piece_off(it);
+            *reinterpret_cast<float4*>(la + off) = lo_of(*reinterpret_cast<const float4*>(ra + off));
+            *reinterpret_cast<float4*>(lb + off) = lo_of(*reinterpret_cast<const float4*>(rb + off));
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (t == 0) {
+            const uint64_t dAhi = make_sw128_desc(smem_u32(ra)), dAlo = make_sw128_desc(smem_u32(la));
+            const uint64_t dBhi = make_sw128_desc(smem_u32(rb)), dBlo = make_sw128_desc(smem_u32(lb));
+#pragma unroll
+            for (int kk = 0; kk < MmaSmem::kChunkK / 8; kk++) {
+                const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+                const uint32_t first = (chunk == 0 && kk == 0) ? 0u : 1u;
+                umma_tf32(tmem_d, dAlo + adv, dBhi + adv, kIdescTf32, first);
+                umma_tf32(tmem_d, dAhi + adv, dBlo + adv, kIdescTf32, 1u);
+                umma_tf32(tmem_d, dAhi + adv, dBhi + adv, kIdescTf32, 1u);
+            }
+            umma_commit(bar);
+        }
+        mbar_wait(bar, (uint32_t)(chunk & 1));
+        tc_fence_after();
+        if (chunk + 1 < kChunks) issue_loads(chunk + 1);
+    }
+    {
+        float* stage = reinterpret_cast<float*>(smem);
+        const int drow = (warp & 3) * 32 + lane;
+        const int dcol0 = (warp >> 2) * 64;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            float acc[32];
+            const int col = dcol0 + h * 32;
+            tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col, acc);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int c4 = (col >> 2) + q;
+                *reinterpret_cast<float4*>(stage + drow * 128 + ((c4 ^ (drow & 7)) << 2)) =
+                    make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            }
+        }
+        __syncthreads();
+        const long coff = b * g.strideC + (long)tr * NB * g.ldc + (long)tc * NB;
+#pragma unroll 4
+        for (int rr = 0; rr < 16; rr++) {
+            const int row = warp * 16 + rr;
+            const float4 d = *reinterpret_cast<const float4*>(stage + row * 128 + ((lane ^ (row & 7)) << 2));
+            float4 v = d;
+            if constexpr (SUB) {
+                v = *(reinterpret_cast<const float4*>(g.Csrc + coff + (long)row * g.ldc) + lane);
+                v.x -= d.x, v.y -= d.y, v.z -= d.z, v.w -= d.w;
+            }
+            *(reinterpret_cast<float4*>(g.Cdst + coff + (long)row * g.ldc) + lane) = v;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, 128);
+}
+
+struct PivCand {
+    float v;
+    int i;
+};
+__device__ __forceinline__ PivCand piv_better(PivCand a, PivCand b) {
+    return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+
+// Panel factorisation: one CTA of 1024 threads per matrix, thread t = row o + t of the working matrix.
+__global__ void __launch_bounds__(1024, 1)
+lu_panel_kernel(float* __restrict__ Wk, float* __restrict__ L, int* __restrict__ P, int n, int o) {
+    __shared__ float urow[32];       // pivot row, columns kk.. of the sub-panel
+    __shared__ float krow[32];       // the row that sat at position k before the exchange
+    __shared__ PivCand red[32];
+    __shared__ int spiv[32];         // pivots of the current sub-panel (absolute row indices)
+    __shared__ float l11[32][33];    // multipliers of the sub-panel's own 32 rows
+    __shared__ __align__(16) float ublk[32][96];  // U rows of the sub-panel for the columns right of it
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int R = n - o;             // rows of the panel
+    const int row = o + t;
+    const bool live = t < R;
+    float* wk = Wk + (long)blockIdx.x * n * n;
+    float* lm = L + (long)blockIdx.x * n * n;
+    int* pv = P + (long)blockIdx.x * n;
+    for (int sp = 0; sp < 4; sp++) {
+        const int cs = o + 32 * sp;  // first column of the sub-panel
+        float a[32];
+        if (live) {
+            const float4* src = reinterpret_cast<const float4*>(wk + (long)row * n + cs);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                float4 v = src[q];
+                a[4 * q] = v.x, a[4 * q + 1] = v.y, a[4 * q + 2] = v.z, a[4 * q + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 32; q++) a[q] = 0.0f;
+        }
+        static_for<0, 32>([&](auto kkc) {
+            constexpr int kk = decltype(kkc)::value;
+            const int k = cs + kk;  // pivot position (absolute row = absolute column)
+            int p = k;
+            if (k < n - 1) {
+                PivCand c{-2.0f, 0x7fffffff};
+                if (live && row >= k) {
+                    float v = fabsf(a[kk]);
+                    if (v != v) v = (row == k) ? __int_as_float(0x7f800000) : -1.0f;
+                    c = PivCand{v, row};
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    PivCand o2{__shfl_xor_sync(0xffffffffu, c.v, off), __shfl_xor_sync(0xffffffffu, c.i, off)};
+                    c = piv_better(c, o2);
+                }
+                if (lane == 0) red[warp] = c;
+                __syncthreads();
+                if (warp == 0) {
+                    PivCand c2 = red[lane];
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        PivCand o2{__shfl_xor_sync(0xffffffffu, c2.v, off), __shfl_xor_sync(0xffffffffu, c2.i, off)};
+                        c2 = piv_better(c2, o2);
+                    }
+                    if (lane == 0) {
+                        red[0] = c2;
+                        spiv[kk] = c2.i;
+                        pv[k] = c2.i;
+                    }
+                }
+                __syncthreads();
+                p = red[0].i;
+            } else if (t == 0) {
+                spiv[kk] = k;
+                pv[k] = k;
+            }
+            // whole rows are exchanged (multipliers included, LAPACK style: the deferred block updates below
+            // need L in final row order; lu_unswap_kernel restores the reference's convention at the end)
+            if (live && row == p) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) urow[j] = a[j];
+            }
+            if (live && row == k && p != k) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) krow[j] = a[j];
+            }
+            __syncthreads();
+            if (live && p != k) {
+                if (row == k) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) a[j] = urow[j];
+                } else if (row == p) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) a[j] = krow[j];
+                }
+            }
+            if (live && row > k) {
+                const float l = a[kk] / urow[kk];
+                a[kk] = l;
+#pragma unroll
+                for (int j = kk + 1; j < 32; j++) a[j] = fmaf(-l, urow[j], a[j]);
+            }
+            __syncthreads();  // urow / krow / red are reused by the next column
+        });
+        // write the sub-panel: multipliers to L (unit diagonal, zeros above), U11 entries to the working matrix
+        if (live) {
+            float4* wdst = reinterpret_cast<float4*>(wk + (long)row * n + cs);
+            float4* ldst = reinterpret_cast<float4*>(lm + (long)row * n + cs);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                float u[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int c = cs + 4 * q + e;
+                    const float v = a[4 * q + e];
+                    u[e] = (row <= c) ? v : 0.0f;
+                    l[e] = (row > c) ? v : (row == c ? 1.0f : 0.0f);
+                }
+                wdst[q] = make_float4(u[0], u[1], u[2], u[3]);
+                ldst[q] = make_float4(l[0], l[1], l[2], l[3]);
+            }
+            if (row >= cs && row < cs + 32) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) l11[row - cs][j] = a[j];
+            }
+        }
+        const int rem0 = cs + 32, nrem = o + NB - rem0;  // columns of the panel right of the sub-panel
+        __syncthreads();
+        // the sub-panel's row exchanges on the panel columns LEFT of it (multipliers already in the L buffer)
+        if (t >= 96 && t < 96 + (cs - o)) {
+            float* col = lm + o + (t - 96);
+            for (int kk = 0; kk < 32; kk++) {
+                const int k = cs + kk, p = spiv[kk];
+                if (p != k) {
+                    const float x = col[(long)k * n], y = col[(long)p * n];
+                    col[(long)k * n] = y;
+                    col[(long)p * n] = x;
+                }
+            }
+        }
+        if (nrem > 0) {
+            // 1. the sub-panel's row exchanges on those columns (one thread per column, in pivot order)
+            if (t < nrem) {
+                float* col = wk + rem0 + t;
+                for (int kk = 0; kk < 32; kk++) {
+                    const int k = cs + kk, p = spiv[kk];
+                    if (p != k) {
+                        const float x = col[(long)k * n], y = col[(long)p * n];
+                        col[(long)k * n] = y;
+                        col[(long)p * n] = x;
+                    }
+                }
+                // 2. U rows of the sub-panel: forward substitution with the unit-lower 32 x 32 block
+                float x[32];
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    float s = col[(long)(cs + i) * n];
+#pragma unroll
+                    for (int kk = 0; kk < i; kk++) s = fmaf(-l11[i][kk], x[kk], s);
+                    x[i] = s;
+                    col[(long)(cs + i) * n] = s;
+                    ublk[i][t] = s;
+                }
+            }
+            __syncthreads();
+            // 3. rank-32 update of the rows below the sub-panel
+            if (live && row >= cs + 32) {
+                float4* dst = reinterpret_cast<float4*>(wk + (long)row * n + rem0);
+                for (int q = 0; q < nrem / 4; q++) {
+                    float4 v = dst[q];
+#pragma unroll
+                    for (int kk = 0; kk < 32; kk++) {
+                        const float4 u = *reinterpret_cast<const float4*>(&ublk[kk][4 * q]);
+                        v.x = fmaf(-a[kk], u.x, v.x), v.y = fmaf(-a[kk], u.y, v.y);
+                        v.z = fmaf(-a[kk], u.z, v.z), v.w = fmaf(-a[kk], u.w, v.w);
+                    }
+                    dst[q] = v;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// the panel's 128 row exchanges on the columns right of the panel (working matrix) and on the L columns
+// left of it (L buffer); grid: (ceil((n - 128) / 256), batch): column index x < o -> L column x,
+// else working-matrix column x + 128
+__global__ void __launch_bounds__(256)
+lu_swap_kernel(float* __restrict__ Wk, float* __restrict__ L, const int* __restrict__ P, int n, int o) {
+    __shared__ int piv[NB];
+    if (threadIdx.x < NB) piv[threadIdx.x] = P[(long)blockIdx.y * n + o + threadIdx.x];
+    __syncthreads();
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    if (x >= n - NB) return;
+    float* col = (x < o) ? L + (long)blockIdx.y * n * n + x : Wk + (long)blockIdx.y * n * n + x + NB;
+    for (int kk = 0; kk < NB; kk++) {
+        const int k = o + kk, p = piv[kk];
+        if (p != k) {
+            const float a = col[(long)k * n], b = col[(long)p * n];
+            col[(long)k * n] = b;
+            col[(long)p * n] = a;
+        }
+    }
+}
+
+// Back to the reference's convention: there the multipliers of column c stay where they were computed and
+// are not carried along by the later exchanges k' > c (lu_v1.1/model4x4/lu.cpp:55-63 exchanges columns
+// >= id only).  Undo those exchanges on column c, last one first.  grid: (ceil(n/256), batch)
+__global__ void __launch_bounds__(256)
+lu_unswap_kernel(float* __restrict__ L, const int* __restrict__ P, int n) {
+    extern __shared__ int pall[];
+    for (int i = threadIdx.x; i < n; i += 256) pall[i] = P[(long)blockIdx.y * n + i];
+    __syncthreads();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= n) return;
+    float* col = L + (long)blockIdx.y * n * n + c;
+    for (int k = n - 2; k > c; k--) {
+        const int p = pall[k];
+        if (p != k) {
+            const float a = col[(long)k * n], b = col[(long)p * n];
+            col[(long)k * n] = b;
+            col[(long)p * n] = a;
+        }
+    }
+}
+
+// W = inv(L11), L11 unit lower triangular 128 x 128 (from the L buffer); one CTA of 128 threads per matrix
+__global__ void __launch_bounds__(128)
+lu_inv_kernel(const float* __restrict__ L, float* __restrict__ W, int n, int o) {
+    extern __shared__ __align__(16) float smem_f[];
+    constexpr int ld = NB + 1;
+    float* l = smem_f;
+    float* x = smem_f + NB * ld;
+    const int t = threadIdx.x;
+    const float* blk = L + (long)blockIdx.x * n * n + (long)o * n + o;
+    for (int e = t; e < NB * NB; e += 128) {
+        const int i = e / NB, j = e - i * NB;
+        l[i * ld + j] = blk[(long)i * n + j];
+    }
+    __syncthreads();
+    const int c = t;  // column c of the inverse by forward substitution
+    for (int i = 0; i < NB; i++) {
+        float s = (i == c) ? 1.0f : 0.0f;
+        if (i > c)
+            for (int k = c; k < i; k++) s = fmaf(-l[i * ld + k], x[k * ld + c], s);
+        x[i * ld + c] = (i >= c) ? s : 0.0f;
+    }
+    __syncthreads();
+    float* wout = W + (long)blockIdx.x * NB * NB;
+    for (int e = t; e < NB * NB; e += 128) {
+        const int i = e / NB, j = e - i * NB;
+        wout[e] = x[i * ld + j];
+    }
+}
+
+// T[c][k] = Wk[o + k][o + 128 + c] (gather) or the reverse (scatter); 32 x 32 tiles through shared memory.
+// grid: (ncols / 32, 4, batch), block (32, 8)
+template <int SCATTER>
+__global__ void __launch_bounds__(256)
+lu_transpose_kernel(float* __restrict__ Wk, float* __restrict__ T, int n, int o) {
+    __shared__ float tile[32][33];
+    float* wk = Wk + (long)blockIdx.z * n * n + (long)o * n + o + NB;  // A12: 128 x ncols, ld n
+    float* tt = T + (long)blockIdx.z * n * NB;                          // ncols x 128, ld 128
+    const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    if (!SCATTER) {
+        for (int r = ty; r < 32; r += 8) tile[r][tx] = wk[(long)(k0 + r) * n + c0 + tx];
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) tt[(long)(c0 + r) * NB + k0 + tx] = tile[tx][r];
+    } else {
+        for (int r = ty; r < 32; r += 8) tile[r][tx] = tt[(long)(c0 + r) * NB + k0 + tx];
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) wk[(long)(k0 + r) * n + c0 + tx] = tile[tx][r];
+    }
+}
+
+cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long batch, cudaStream_t st) {
+    if (n % NB != 0 || n < 2 * NB || n > 1024) return cudaErrorNotSupported;
+    if ((((uintptr_t)A | (uintptr_t)L | (uintptr_t)U) & 15) != 0) return cudaErrorNotSupported;
+    if (batch == 0) return cudaSuccess;
+    if (batch > 65535) return cudaErrorNotSupported;
+    cudaError_t e;
+    float *Winv = nullptr, *T0 = nullptr, *T1 = nullptr;
+    if ((e = cudaMallocAsync(&Winv, sizeof(float) * (size_t)batch * NB * NB, st)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(&T0, sizeof(float) * (size_t)batch * n * NB, st)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(&T1, sizeof(float) * (size_t)batch * n * NB, st)) != cudaSuccess) return e;
+    const size_t inv_smem = 2 * NB * (NB + 1) * sizeof(float);
+    cudaFuncSetAttribute(lu_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem);
+    cudaFuncSetAttribute(gemm_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
+    cudaFuncSetAttribute(gemm_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
+    const unsigned nb = (unsigned)batch;
+    const long nn = (long)n * n;
+    if ((e = cudaMemcpyAsync(U, A, sizeof(float) * (size_t)batch * nn, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
+    const int panels = n / NB;
+    blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, nb), 256, 0, st>>>(L, n);
+    count_launch();
+    for (int p = 0; p < panels; p++) {
+        const int o = p * NB;
+        const int mt = panels - p - 1, ncols = mt * NB;
+        lu_panel_kernel<<<nb, 1024, 0, st>>>(U, L, P, n, o);
+        count_launch();
+        if (mt == 0) {  // last panel: only the L columns left of it still have to follow its exchanges
+            lu_swap_kernel<<<dim3((n - NB + 255) / 256, nb), 256, 0, st>>>(U, L, P, n, o);
+            count_launch();
+            break;
+        }
+        lu_swap_kernel<<<dim3((n - NB + 255) / 256, nb), 256, 0, st>>>(U, L, P, n, o);
+        count_launch();
+        lu_inv_kernel<<<nb, 128, inv_smem, st>>>(L, Winv, n, o);
+        count_launch();
+        lu_transpose_kernel<0><<<dim3(ncols / 32, 4, nb), dim3(32, 8), 0, st>>>(U, T0, n, o);
+        count_launch();
+        TileArgs g{};
+        g.A = T0, g.lda = NB, g.strideA = (long)n * NB;
+        g.B = Winv, g.ldb = NB, g.strideB = (long)NB * NB;
+        g.Csrc = T1, g.Cdst = T1, g.ldc = NB, g.strideC = (long)n * NB;
+        g.tiles_col = 1;
+        gemm_tile_kernel<0><<<dim3(mt, nb), 256, MmaSmem::kTotal, st>>>(g);
+        count_launch();
+        lu_transpose_kernel<1><<<dim3(ncols / 32, 4, nb), dim3(32, 8), 0, st>>>(U, T1, n, o);
+        count_launch();
+        TileArgs h{};
+        h.A = L + (long)(o + NB) * n + o, h.lda = n, h.strideA = nn;
+        h.B = T1, h.ldb = NB, h.strideB = (long)n * NB;
+        h.Csrc = U + (long)(o + NB) * n + (o + NB), h.Cdst = U + (long)(o + NB) * n + (o + NB), h.ldc = n, h.strideC = nn;
+        h.tiles_col = mt;
+        gemm_tile_kernel<1><<<dim3(mt * mt, nb), 256, MmaSmem::kTotal, st>>>(h);
+        count_launch();
+    }
+    lu_unswap_kernel<<<dim3((n + 255) / 256, nb), 256, n * sizeof(int), st>>>(L, P, n);
+    count_launch();
+    e = cudaGetLastError();
+    cudaFreeAsync(Winv, st);
+    cudaFreeAsync(T0, st);
+    cudaFreeAsync(T1, st);
+    return e;
+}
+
 }  // namespace hlsd

@@ -99,8 +99,17 @@ static int lu_dev(const float* A, float* L, float* U, int32_t* P, int n, int64_t
     if (n < 1 || batch < 0) return fail(HLSD_ERR_INVALID, "n must be >= 1 and batch >= 0");
     if (!lu_pivoting(design, &pivoting)) return fail(HLSD_ERR_INVALID, "unknown LU design");
     if (int rc = check_path(flags, &path)) return rc;
-    if (path == HLSD_PATH_BLOCKED || path == HLSD_PATH_TENSOR)
-        return fail(HLSD_ERR_UNSUPPORTED, "blocked LU is not built in this version");
+    if (path == HLSD_PATH_AUTO && pivoting && n >= 256 && n <= 1024 && n % 128 == 0 && batch <= 65535 &&
+        (((uintptr_t)A | (uintptr_t)L | (uintptr_t)U) & 15) == 0)
+        path = HLSD_PATH_TENSOR;
+    if (path == HLSD_PATH_BLOCKED) return fail(HLSD_ERR_UNSUPPORTED, "HLSD_PATH_BLOCKED (SIMT trailing update) is not built; use HLSD_PATH_TENSOR or HLSD_PATH_GLOBAL");
+    if (path == HLSD_PATH_TENSOR) {
+        if (!pivoting) return fail(HLSD_ERR_UNSUPPORTED, "the blocked LU implements the pivoted designs only");
+        cudaError_t e = lu_blocked(A, L, U, P, n, (long)batch, st);
+        if (e == cudaErrorNotSupported) return fail(HLSD_ERR_UNSUPPORTED, "the blocked tensor-core LU needs n % 128 == 0, 256 <= n <= 1024, batch <= 65535");
+        if (e != cudaSuccess) return cuda_fail(e, "lu_blocked");
+        return 0;
+    }
     cudaError_t e = lu_exact(A, L, U, P, n, (long)batch, pivoting, path, st);
     if (e == cudaErrorInvalidValue) return fail(HLSD_ERR_UNSUPPORTED, "requested kernel path cannot serve this size/alignment");
     if (e != cudaSuccess) return cuda_fail(e, "lu");

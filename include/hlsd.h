@@ -68,7 +68,8 @@ typedef enum {
 #define HLSD_PATH_GROUP 2   /* warp/CTA per matrix, shared-memory resident                     */
 #define HLSD_PATH_GLOBAL 3  /* one CTA per matrix in global memory: any N, exact, slow         */
 #define HLSD_PATH_BLOCKED 4 /* blocked right-looking, fp32 SIMT trailing update (exact order)  */
-#define HLSD_PATH_TENSOR 5  /* blocked right-looking, tcgen05 tensor-core trailing update      */
+#define HLSD_PATH_TENSOR 5  /* blocked right-looking, tcgen05 tensor-core trailing update:
+                               Cholesky n >= 256, n % 128 == 0; LU 256 <= n <= 1024, n % 128 == 0     */
 #define HLSD_PATH_MASK 0xff
 
 /* ---- host-pointer entry points (the reference's top(), batched) ---- */
