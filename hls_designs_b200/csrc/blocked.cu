@@ -463,10 +463,11 @@ cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int us
 //     1. lu_panel_kernel   (SIMT) pivoted elimination of the (N-o) x 128 panel, thread = row, in four
 //                          32-column sub-panels held in registers; writes L (unit lower) to the L
 //                          buffer, U11 to the working matrix, the pivots to P
-//     2. lu_swap_kernel    (SIMT) the panel's row exchanges applied to the columns right of the panel and,
-//                          LAPACK style, to the L columns left of it (the deferred block updates need L in
-//                          final row order); lu_unswap_kernel converts L back to the reference's convention
-//                          (multipliers stay where they were computed) at the very end
+//     2. lu_swap_kernel    (SIMT) the panel's row exchanges applied to the columns right of the panel
+//     8. lu_unswap_panel_kernel (SIMT) inside a panel rows are exchanged whole (the deferred block updates
+//                          need L in final row order); once L21 has served as operand, the panel's L
+//                          columns go back to the reference's convention (multipliers stay where they
+//                          were computed); exchanges of later panels never touch them
 //     3. lu_inv_kernel     (SIMT) W = inv(L11), unit lower triangular
 //     4. lu_gather_kernel  (SIMT) T0 = A12^T  (k contiguous: the tensor core wants K-major operands)
 //     5. gemm_tile_kernel<0> (tcgen05) T1 = T0 * W^T = U12^T
@@ -597,7 +598,8 @@ __device__ __forceinline__ PivCand piv_better(PivCand a, PivCand b) {
     return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
 }
 
-// Panel factorisation: one CTA of 1024 threads per matrix, thread t = row o + t of the working matrix.
+// Panel factorisation: one CTA per matrix, thread t = row o + t of the working matrix (blockDim = rows of
+// the panel, at least 256 because threads 0..191 also serve as column workers between sub-panels).
 __global__ void __launch_bounds__(1024, 1)
 lu_panel_kernel(float* __restrict__ Wk, float* __restrict__ L, int* __restrict__ P, int n, int o) {
     __shared__ float urow[32];       // pivot row, columns kk.. of the sub-panel
@@ -646,7 +648,7 @@ lu_panel_kernel(float* __restrict__ Wk, float* __restrict__ L, int* __restrict__
                 if (lane == 0) red[warp] = c;
                 __syncthreads();
                 if (warp == 0) {
-                    PivCand c2 = red[lane];
+                    PivCand c2 = lane < (int)(blockDim.x >> 5) ? red[lane] : PivCand{-2.0f, 0x7fffffff};
 #pragma unroll
                     for (int off = 16; off > 0; off >>= 1) {
                         PivCand o2{__shfl_xor_sync(0xffffffffu, c2.v, off), __shfl_xor_sync(0xffffffffu, c2.i, off)};
@@ -665,7 +667,7 @@ lu_panel_kernel(float* __restrict__ Wk, float* __restrict__ L, int* __restrict__
                 pv[k] = k;
             }
             // whole rows are exchanged (multipliers included, LAPACK style: the deferred block updates below
-            // need L in final row order; lu_unswap_kernel restores the reference's convention at the end)
+            // need L in final row order; lu_unswap_panel_kernel restores the reference's convention afterwards)
             if (live && row == p) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) urow[j] = a[j];
@@ -772,45 +774,97 @@ lu_panel_kernel(float* __restrict__ Wk, float* __restrict__ L, int* __restrict__
     }
 }
 
-// the panel's 128 row exchanges on the columns right of the panel (working matrix) and on the L columns
-// left of it (L buffer); grid: (ceil((n - 128) / 256), batch): column index x < o -> L column x,
-// else working-matrix column x + 128
-__global__ void __launch_bounds__(256)
-lu_swap_kernel(float* __restrict__ Wk, float* __restrict__ L, const int* __restrict__ P, int n, int o) {
-    __shared__ int piv[NB];
-    if (threadIdx.x < NB) piv[threadIdx.x] = P[(long)blockIdx.y * n + o + threadIdx.x];
-    __syncthreads();
-    const int x = blockIdx.x * 256 + threadIdx.x;
-    if (x >= n - NB) return;
-    float* col = (x < o) ? L + (long)blockIdx.y * n * n + x : Wk + (long)blockIdx.y * n * n + x + NB;
+// Slots of the rows a panel's 128 exchanges touch: slots 0..127 are positions o..o+127, further slots are
+// the distinct pivot rows below the panel.  pslot[kk] = slot of P[o + kk].  Returns the slot count.
+__device__ __forceinline__ int lu_touched_rows(const int* piv, int o, int* pos, int* pslot) {
+    int cnt = NB;
+    for (int kk = 0; kk < NB; kk++) pos[kk] = o + kk;
     for (int kk = 0; kk < NB; kk++) {
-        const int k = o + kk, p = piv[kk];
-        if (p != k) {
-            const float a = col[(long)k * n], b = col[(long)p * n];
-            col[(long)k * n] = b;
-            col[(long)p * n] = a;
+        const int p = piv[kk];
+        int sp = -1;
+        if (p < o + NB) sp = p - o;
+        else {
+            for (int q = NB; q < cnt; q++)
+                if (pos[q] == p) sp = q;
+            if (sp < 0) {
+                sp = cnt;
+                pos[cnt++] = p;
+            }
         }
+        pslot[kk] = sp;
     }
+    return cnt;
 }
 
-// Back to the reference's convention: there the multipliers of column c stay where they were computed and
-// are not carried along by the later exchanges k' > c (lu_v1.1/model4x4/lu.cpp:55-63 exchanges columns
-// >= id only).  Undo those exchanges on column c, last one first.  grid: (ceil(n/256), batch)
-__global__ void __launch_bounds__(256)
-lu_unswap_kernel(float* __restrict__ L, const int* __restrict__ P, int n) {
-    extern __shared__ int pall[];
-    for (int i = threadIdx.x; i < n; i += 256) pall[i] = P[(long)blockIdx.y * n + i];
+// The panel's 128 row exchanges on the columns right of the panel (working matrix).  The exchanges are
+// first composed into "slot q receives the old row of slot src[q]" (one thread, shared memory), then every
+// thread moves its column with independent loads followed by independent stores instead of 128 dependent
+// exchange steps.  grid: (ceil(ncols / 128), batch), 128 threads
+__global__ void __launch_bounds__(128)
+lu_swap_kernel(float* __restrict__ Wk, const int* __restrict__ P, int n, int o) {
+    __shared__ int piv[NB], pos[2 * NB], pslot[NB], src[2 * NB];
+    __shared__ int ntouch;
+    piv[threadIdx.x] = P[(long)blockIdx.y * n + o + threadIdx.x];
     __syncthreads();
-    const int c = blockIdx.x * 256 + threadIdx.x;
-    if (c >= n) return;
-    float* col = L + (long)blockIdx.y * n * n + c;
-    for (int k = n - 2; k > c; k--) {
-        const int p = pall[k];
-        if (p != k) {
-            const float a = col[(long)k * n], b = col[(long)p * n];
-            col[(long)k * n] = b;
-            col[(long)p * n] = a;
+    if (threadIdx.x == 0) {
+        const int cnt = lu_touched_rows(piv, o, pos, pslot);
+        for (int q = 0; q < cnt; q++) src[q] = q;
+        for (int kk = 0; kk < NB; kk++) {
+            const int sp = pslot[kk], tmp = src[kk];
+            src[kk] = src[sp];
+            src[sp] = tmp;
         }
+        ntouch = cnt;
+    }
+    __syncthreads();
+    const int j = o + NB + blockIdx.x * 128 + threadIdx.x;
+    if (j >= n) return;
+    float* col = Wk + (long)blockIdx.y * n * n + j;
+    const int cnt = ntouch;
+    float buf[2 * NB];  // per-thread staging (local memory, L1-resident): all reads precede all writes
+    for (int q = 0; q < cnt; q++) buf[q] = col[(long)pos[src[q]] * n];
+    for (int q = 0; q < cnt; q++)
+        if (src[q] != q) col[(long)pos[q] * n] = buf[q];
+}
+
+// Back to the reference's convention for the panel's own 128 L columns.  Inside the panel rows were
+// exchanged whole (the deferred block updates need L in final row order); in the reference the multipliers
+// of column c stay where they were computed and are not carried along by later exchanges
+// (lu_v1.1/model4x4/lu.cpp:55-63 exchanges columns >= id only).  Undo, per column c, the panel's exchanges
+// k' > c, last one first; exchanges of later panels never touch these columns.  The touched rows
+// (<= 256) x 128 columns are staged in shared memory.  grid: (batch), 256 threads
+__global__ void __launch_bounds__(256)
+lu_unswap_panel_kernel(float* __restrict__ L, const int* __restrict__ P, int n, int o) {
+    extern __shared__ __align__(16) float us_tile[];  // [2 * NB][NB + 1]
+    __shared__ int piv[NB], pos[2 * NB], pslot[NB];
+    __shared__ int ntouch;
+    constexpr int ld = NB + 1;
+    if (threadIdx.x < NB) piv[threadIdx.x] = P[(long)blockIdx.x * n + o + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) ntouch = lu_touched_rows(piv, o, pos, pslot);
+    __syncthreads();
+    const int cnt = ntouch;
+    float* base = L + (long)blockIdx.x * n * n + o;
+    for (int e = threadIdx.x; e < cnt * NB; e += 256) {
+        const int q = e >> 7, c = e & (NB - 1);
+        us_tile[q * ld + c] = base[(long)pos[q] * n + c];
+    }
+    __syncthreads();
+    if (threadIdx.x < NB) {
+        const int c = threadIdx.x;  // column o + c: undo exchanges kk = 127 .. c+1
+        for (int kk = NB - 1; kk > c; kk--) {
+            const int sp = pslot[kk];
+            if (sp != kk) {
+                const float a = us_tile[kk * ld + c], b = us_tile[sp * ld + c];
+                us_tile[kk * ld + c] = b;
+                us_tile[sp * ld + c] = a;
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < cnt * NB; e += 256) {
+        const int q = e >> 7, c = e & (NB - 1);
+        base[(long)pos[q] * n + c] = us_tile[q * ld + c];
     }
 }
 
@@ -875,6 +929,8 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
     if ((e = cudaMallocAsync(&T0, sizeof(float) * (size_t)batch * n * NB, st)) != cudaSuccess) return e;
     if ((e = cudaMallocAsync(&T1, sizeof(float) * (size_t)batch * n * NB, st)) != cudaSuccess) return e;
     const size_t inv_smem = 2 * NB * (NB + 1) * sizeof(float);
+    const size_t unswap_smem = (size_t)2 * NB * (NB + 1) * sizeof(float);
+    cudaFuncSetAttribute(lu_unswap_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)unswap_smem);
     cudaFuncSetAttribute(lu_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem);
     cudaFuncSetAttribute(gemm_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
     cudaFuncSetAttribute(gemm_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
@@ -887,14 +943,15 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
     for (int p = 0; p < panels; p++) {
         const int o = p * NB;
         const int mt = panels - p - 1, ncols = mt * NB;
-        lu_panel_kernel<<<nb, 1024, 0, st>>>(U, L, P, n, o);
+        // thread = row of the panel: later panels are shorter and run with fewer (cheaper to synchronise) threads
+        lu_panel_kernel<<<nb, std::max(256, n - o), 0, st>>>(U, L, P, n, o);
         count_launch();
-        if (mt == 0) {  // last panel: only the L columns left of it still have to follow its exchanges
-            lu_swap_kernel<<<dim3((n - NB + 255) / 256, nb), 256, 0, st>>>(U, L, P, n, o);
+        if (mt == 0) {  // last panel: nothing to update, only its L columns go back to the reference's convention
+            lu_unswap_panel_kernel<<<nb, 256, unswap_smem, st>>>(L, P, n, o);
             count_launch();
             break;
         }
-        lu_swap_kernel<<<dim3((n - NB + 255) / 256, nb), 256, 0, st>>>(U, L, P, n, o);
+        lu_swap_kernel<<<dim3((ncols + 127) / 128, nb), 128, 0, st>>>(U, P, n, o);
         count_launch();
         lu_inv_kernel<<<nb, 128, inv_smem, st>>>(L, Winv, n, o);
         count_launch();
@@ -916,9 +973,9 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
         h.tiles_col = mt;
         gemm_tile_kernel<1><<<dim3(mt * mt, nb), 256, MmaSmem::kTotal, st>>>(h);
         count_launch();
+        lu_unswap_panel_kernel<<<nb, 256, unswap_smem, st>>>(L, P, n, o);  // L21 has served as operand
+        count_launch();
     }
-    lu_unswap_kernel<<<dim3((n + 255) / 256, nb), 256, n * sizeof(int), st>>>(L, P, n);
-    count_launch();
     e = cudaGetLastError();
     cudaFreeAsync(Winv, st);
     cudaFreeAsync(T0, st);
