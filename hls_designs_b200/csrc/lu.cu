@@ -8,6 +8,8 @@
 //   lu_tpm_kernel<N>      thread-per-matrix in registers, N in {4, 8}: bulk-copy staged slabs.
 //   lu_group_kernel<G>    G threads per matrix, matrix resident in shared memory.
 //   lu_global_kernel      one CTA per matrix, in place in global memory (any N; exact; slow).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -309,6 +311,134 @@ lu_rows_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// One lane per row (N = 32: one warp per matrix, N = 64: two warps per matrix): the same scheme as
+// lu_rows_kernel with a single data row per lane, which removes the per-lane row selection from the
+// pivot-row broadcast and halves the register tile.  Two barriers per column (after the pivot
+// search partials, after the pivot row is published), named barriers for the two-warp case.
+// ------------------------------------------------------------------------------------------------
+template <int N, int MATS>
+__global__ void __launch_bounds__(MATS * N, 1)
+lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restrict__ U, int* __restrict__ P,
+               long batch, int pivoting) {
+    static_assert(N == 32 || N == 64, "one or two warps per matrix");
+    constexpr int WPM = N / 32;  // warps per matrix
+    constexpr int kSlot = N * N + 4;
+    constexpr int kStrip = 9;    // 8 block columns + 1: lanes fall on distinct banks
+    constexpr int kStripAll = (N * kStrip + 3) / 4 * 4;
+    constexpr int kPerMat = 2 * kSlot + kStripAll + N + 8;  // floats: A/L slab, U slab, strips, P, partials
+    constexpr uint32_t kRowBytes = N * 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* base = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)MATS * kPerMat * 4);
+    const int mat = threadIdx.x / N, r = threadIdx.x % N, lane = threadIdx.x & 31;
+    float* sA = base + (size_t)mat * kPerMat;
+    float* sU = sA + kSlot;
+    float* sp = sU + kSlot + r * kStrip;
+    int* sP = reinterpret_cast<int*>(sU + kSlot + kStripAll);
+    PivotCand* part = reinterpret_cast<PivotCand*>(sP + N);  // [2 parities][WPM]
+    uint64_t* bar = bars + mat;
+    auto gsync = [&]() {
+        if constexpr (WPM == 1) __syncwarp();
+        else named_bar_sync(1 + mat, N);
+    };
+    if (r == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    gsync();
+    uint32_t parity = 0;
+    for (long b = (long)blockIdx.x * MATS + mat; b < batch; b += (long)gridDim.x * MATS) {
+        bulk_wait_read<0>();
+        gsync();
+        if (r == 0) mbar_arrive_expect_tx(bar, N * kRowBytes);
+        gsync();
+        bulk_g2s(sA + r * N, A + b * (long)(N * N) + r * N, kRowBytes, bar);
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        float a[N];
+        {
+            const float4* row4 = reinterpret_cast<const float4*>(sA + r * N);
+#pragma unroll
+            for (int q = 0; q < N / 4; q++) {
+                float4 v = row4[q];
+                a[4 * q] = v.x, a[4 * q + 1] = v.y, a[4 * q + 2] = v.z, a[4 * q + 3] = v.w;
+            }
+        }
+        gsync();  // operand in registers: the slab becomes L (identity), the other one U (zero)
+        {
+            float4* l4 = reinterpret_cast<float4*>(sA + r * N);
+            float4* u4 = reinterpret_cast<float4*>(sU + r * N);
+#pragma unroll
+            for (int q = 0; q < N / 4; q++) {
+                l4[q] = make_float4(r == 4 * q ? 1.0f : 0.0f, r == 4 * q + 1 ? 1.0f : 0.0f, r == 4 * q + 2 ? 1.0f : 0.0f,
+                                    r == 4 * q + 3 ? 1.0f : 0.0f);
+                u4[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+        }
+        int pos = r;
+        gsync();
+        static_for<0, N / 8>([&](auto kbc) {
+            constexpr int KB = decltype(kbc)::value;
+            constexpr int c0 = 8 * KB;
+#pragma unroll
+            for (int q = 0; q < 8; q++) sp[q] = a[c0 + q];
+            for (int kr = 0; kr < 8; kr++) {
+                const int k = c0 + kr;
+                int p = k;
+                if (pivoting && k < N - 1) {
+                    PivotCand c{-2.0f, 0x7fffffff};
+                    if (pos >= k) c = PivotCand{pivot_key(sp[kr], pos == k), pos};
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        PivotCand o{__shfl_xor_sync(0xffffffffu, c.v, off), __shfl_xor_sync(0xffffffffu, c.i, off)};
+                        c = pivot_better(c, o);
+                    }
+                    if constexpr (WPM == 2) {
+                        PivotCand* pp = part + (k & 1) * 2;
+                        if (lane == 0) pp[r >> 5] = c;
+                        gsync();
+                        c = pivot_better(pp[0], pp[1]);
+                    }
+                    p = c.i;
+                }
+                if (r == 0) sP[k] = p;
+                if (pos == p) pos = k;
+                else if (pos == k) pos = p;
+                float* urow = sU + k * N;
+                if (pos == k) {  // this lane holds the pivot row: publish columns >= k as row k of U
+                    for (int q = kr; q < 8; q++) urow[c0 + q] = sp[q];
+#pragma unroll
+                    for (int j = c0 + 8; j < N; j += 4)
+                        *reinterpret_cast<float4*>(urow + j) = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+                }
+                gsync();
+                if (pos > k) {
+                    const float lm = xdiv(sp[kr], urow[k]);
+                    sA[pos * N + k] = lm;
+                    for (int q = kr + 1; q < 8; q++) sp[q] = xmsub(sp[q], lm, urow[c0 + q]);
+#pragma unroll
+                    for (int j = c0 + 8; j < N; j += 4) {
+                        const float4 u = *reinterpret_cast<const float4*>(urow + j);
+                        a[j] = xmsub(a[j], lm, u.x);
+                        a[j + 1] = xmsub(a[j + 1], lm, u.y);
+                        a[j + 2] = xmsub(a[j + 2], lm, u.z);
+                        a[j + 3] = xmsub(a[j + 3], lm, u.w);
+                    }
+                }
+                if constexpr (WPM == 1) __syncwarp();
+            }
+        });
+        fence_async_smem();
+        gsync();
+        bulk_s2g(L + b * (long)(N * N) + r * N, sA + r * N, kRowBytes);
+        bulk_s2g(U + b * (long)(N * N) + r * N, sU + r * N, kRowBytes);
+        if (r == 0) bulk_s2g(P + b * (long)N, sP, N * 4);
+        bulk_commit();
+    }
+    bulk_wait_read<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
 // shared body: elimination of one matrix `w` (leading dimension ld) by a group of G threads.
 // SYNC() must order all G threads; `red` is scratch for the pivot reduction (G/32 candidates).
 // ------------------------------------------------------------------------------------------------
@@ -448,6 +578,21 @@ static cudaError_t launch_lu_rows(const float* A, float* L, float* U, int* P, lo
     return cudaGetLastError();
 }
 
+template <int N>
+static cudaError_t launch_lu_lane(const float* A, float* L, float* U, int* P, long batch, int pivoting, cudaStream_t st) {
+    constexpr size_t per_mat = (size_t)(2 * (N * N + 4) + (N * 9 + 3) / 4 * 4 + N + 8) * 4;
+    constexpr int fit = (int)((227 * 1024 - 1024) / (per_mat + 8));
+    constexpr int MATS = fit * N > 1024 ? 1024 / N : fit;
+    const size_t smem = MATS * per_mat + MATS * sizeof(uint64_t);
+    auto kern = lu_lane_kernel<N, MATS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long grid = std::min<long>((batch + MATS - 1) / MATS, (long)sm_count());
+    kern<<<(unsigned)grid, MATS * N, smem, st>>>(A, L, U, P, batch, pivoting);
+    count_launch();
+    return cudaGetLastError();
+}
+
 template <int G>
 static cudaError_t launch_lu_group(const float* A, float* L, float* U, int* P, int n, long batch, int pivoting,
                                    cudaStream_t st) {
@@ -463,6 +608,16 @@ static cudaError_t launch_lu_group(const float* A, float* L, float* U, int* P, i
     return cudaGetLastError();
 }
 
+// HLSD_LU_ROWS=1 (environment) selects the two-rows-per-lane kernel for N = 32/64 (A/B measurements)
+static int lu_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("HLSD_LU_ROWS");
+        mode = e ? atoi(e) : 0;
+    }
+    return mode;
+}
+
 cudaError_t lu_exact(const float* A, float* L, float* U, int* P, int n, long batch, int pivoting, int path,
                      cudaStream_t st) {
     if (batch == 0) return cudaSuccess;
@@ -471,8 +626,10 @@ cudaError_t lu_exact(const float* A, float* L, float* U, int* P, int n, long bat
         if (aligned && n == 4) return launch_lu_tpm<4>(A, L, U, P, batch, pivoting, st);
         if (aligned && n == 8) return launch_lu_tpm<8>(A, L, U, P, batch, pivoting, st);
         if (aligned && n == 16) return launch_lu_rows<16, 4>(A, L, U, P, batch, pivoting, st);
-        if (aligned && n == 32) return launch_lu_rows<32, 16>(A, L, U, P, batch, pivoting, st);
-        if (aligned && n == 64) return launch_lu_rows<64, 32>(A, L, U, P, batch, pivoting, st);
+        if (aligned && n == 32) return lu_mode() == 1 ? launch_lu_rows<32, 16>(A, L, U, P, batch, pivoting, st)
+                                                       : launch_lu_lane<32>(A, L, U, P, batch, pivoting, st);
+        if (aligned && n == 64) return lu_mode() == 1 ? launch_lu_rows<64, 32>(A, L, U, P, batch, pivoting, st)
+                                                       : launch_lu_lane<64>(A, L, U, P, batch, pivoting, st);
         if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
     }
     const size_t per = (size_t)n * (n | 1) * 4;

@@ -168,3 +168,39 @@ def test_full_size_cholesky_n16_batch_1m_properties():
     idx = torch.arange(0, batch, batch // 4096, device="cuda")
     want = restate.cholesky(A[idx].cpu().numpy(), threads=8)
     assert bits_equal(L[idx].cpu().numpy(), want)
+
+
+# ---------------------------------------------------------------- randomized sweep over sizes / batches / designs
+def test_random_sweep_bit_exact():
+    """60 random (kind, size, batch, design) draws through the auto dispatch, including odd sizes, batches
+    that are not multiples of a slab, and unaligned device views (which must fall back to a kernel family
+    without alignment requirements): all bit-identical to the oracle."""
+    import torch
+    rng = np.random.default_rng(2026)
+    for it in range(60):
+        kind = ("chol", "lu", "qr")[it % 3]
+        n = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 12, 15, 16, 17, 24, 31, 32, 33, 48, 63, 64, 65, 80]))
+        batch = int(rng.choice([1, 2, 15, 16, 17, 31, 33, 63, 100, 257]))
+        if kind == "chol":
+            d = str(rng.choice(["cholesky_v1.3", "cholesky_v2.2", "cholesky_v3.2", "cholesky_v4.0"]))
+            A = gen_spd(n, batch=batch, seed=it)
+            got, want = [hd.cholesky(A, design=d)], [restate.cholesky(A, d, threads=8)]
+        elif kind == "lu":
+            d = str(rng.choice(["lu_v1.1", "lu_v1.2", "lu_v2.1", "nopivot"]))
+            A = gen_full_rank(n, batch=batch, seed=it) + rng.random((batch, n, n)).astype(np.float32)
+            got, want = hd.lu(A, design=d), restate.lu(A, pivoting=d != "nopivot", threads=8)
+        else:
+            d = str(rng.choice(["qr_v1.1", "qr_v1.2", "qr_v2.1"]))
+            rows = n + int(rng.integers(0, 4))
+            A = gen_full_rank(rows, n, batch=batch, seed=it)
+            got, want = hd.qr(A, design=d), restate.qr(A, d, threads=8)
+        for g, w in zip(got, want):
+            assert bits_equal(g, w), f"draw {it}: {kind} n={n} batch={batch} {d}: {first_mismatch(g, w)}"
+    # device pointers that are only 4-byte aligned (a view one float into a buffer)
+    for n in (16, 64):
+        A = gen_spd(n, batch=40, seed=n)
+        buf = torch.empty(A.size + 1, device="cuda")
+        view = buf[1:].view(40, n, n)
+        view.copy_(torch.from_numpy(A))
+        L = hd.cholesky(view)
+        assert bits_equal(L.cpu().numpy(), restate.cholesky(A))
