@@ -197,15 +197,17 @@ blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __res
             float u[4];
 #pragma unroll
             for (int ib = 0; ib < 4; ib++) u[ib] = ubuf[tc + 32 * ib];
-#pragma unroll
-            for (int ia = KA; ia < 8; ia++) {  // rows i = tr + 16 ia <= k for ia < KA: nothing to do
+            static_for<KA, 8>([&](auto iac) {  // rows i = tr + 16 ia <= k for ia < KA: nothing to do
+                constexpr int ia = decltype(iac)::value;
                 const int i = tr + 16 * ia;
                 if (i > k) {  // warp-uniform
                     const float lr = ubuf[i];
+                    // columns j = tc + 32 ib > i are never needed (both L11 and W are lower triangular):
+                    // i <= 16 ia + 15, so only the slots ib <= ia / 2 can hold j <= i
 #pragma unroll
-                    for (int ib = 0; ib < 4; ib++) v[ia][ib] = fmaf(-lr, u[ib], v[ia][ib]);
+                    for (int ib = 0; ib <= ia / 2; ib++) v[ia][ib] = fmaf(-lr, u[ib], v[ia][ib]);
                 }
-            }
+            });
             // the owner of (k+1, k+1) holds its final value now: take the next square root
             if (k + 1 < NB && tr == ((k + 1) & 15) && tc == ((k + 1) & 31)) {
                 constexpr int KA1 = KA + 1 < 8 ? KA + 1 : 7;
