@@ -29,6 +29,8 @@
 // thread issues 12 tcgen05.mma.kind::tf32 (M128 N128 K8) per chunk; completion is tracked with
 // tcgen05.commit on an mbarrier; the epilogue reads the accumulator with tcgen05.ld (32x32b.x32)
 // and either stores it (TRSM) or subtracts it from C in place (SYRK).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -271,7 +273,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256, MmaSmem::kStages == 1 ? 3 : 2)
 blk_mma_kernel(const float* __restrict__ S, float* __restrict__ L, const float* __restrict__ W, int n, int o) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the address space: LDS/STS, not generic LD/ST)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + MmaSmem::kBar);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + MmaSmem::kTmemPtr);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -422,6 +425,172 @@ blk_mma_kernel(const float* __restrict__ S, float* __restrict__ L, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Left-looking trailing update: tile (r, q) of block column q receives ALL earlier panels at once,
+//      X[r][q] = A[r][q] - sum_{j<q} L[r][j] * L[q][j]^T         (K = 128 q, up to 896)
+// so C is read (from A) and written (to L) once per tile instead of once per panel, and the K loop is
+// long enough to pipeline: cp.async fills a ring of 4 raw stages two chunks ahead, the threads
+// produce the lo tile of chunk c while the tensor core still multiplies chunk c-1 (lo tiles double
+// buffered), completion of chunk c-2 (tcgen05.commit -> one of two mbarriers) frees its buffers.
+// 192 KB of shared memory, one CTA per SM.  grid: (panels - q, batch): r = q + blockIdx.x
+// ------------------------------------------------------------------------------------------------
+struct LlSmem {
+    static constexpr int kTile = 128 * 32 * 4;                 // one operand chunk: 128 rows x 32 k
+    static constexpr int kRaw = 0;                             // [4 stages][A, B]
+    static constexpr int kLo = 8 * kTile;                      // [2][A, B]
+    static constexpr int kBar = 12 * kTile;                    // two mbarriers
+    static constexpr int kTmemPtr = kBar + 16;
+    static constexpr int kTotal = kBar + 32 + 1024;
+};
+
+__global__ void __launch_bounds__(256, 1)
+blk_ll_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) {
+    extern __shared__ unsigned char smem_raw[];
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the address space: LDS/STS, not generic LD/ST)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LlSmem::kBar);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + LlSmem::kTmemPtr);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int r = q + blockIdx.x;
+    float* Lb = L + (long)blockIdx.y * n * n;
+    const float* Sb = S + (long)blockIdx.y * n * n;
+    const float* Arows = Lb + (long)r * NB * n;  // finished panels 0 .. q-1 of block row r
+    const float* Brows = Lb + (long)q * NB * n;  // ... and of block row q
+    const bool same = (r == q);
+    const int C = 4 * q;  // 32-wide K chunks
+
+    if (warp == 0) tmem_alloc(tmem_ptr, 128);
+    if (t == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_ptr;
+
+    auto piece_off = [&](int it) {
+        const int idx = it * 256 + t, row = idx >> 3, c4 = idx & 7;
+        return row * 128 + ((c4 ^ (row & 7)) << 4);
+    };
+    auto issue_loads = [&](int c) {
+        if (c < C) {
+            unsigned char* ra = smem + LlSmem::kRaw + (c & 3) * 2 * LlSmem::kTile;
+            unsigned char* rb = ra + LlSmem::kTile;
+#pragma unroll
+            for (int it = 0; it < 4; it++) {
+                const int idx = it * 256 + t, row = idx >> 3, c4 = idx & 7;
+                cp_async16(ra + piece_off(it), Arows + (long)row * n + c * 32 + c4 * 4);
+                if (!same) cp_async16(rb + piece_off(it), Brows + (long)row * n + c * 32 + c4 * 4);
+            }
+        }
+        cp_async_commit();  // always: keeps the group count uniform
+    };
+    issue_loads(0);
+    issue_loads(1);
+    for (int c = 0; c < C; c++) {
+        if (c >= 2) {  // MMAs of chunk c-2 are done: raw stage (c+2)&3 and lo buffer c&1 are free
+            mbar_wait(&bars[c & 1], (uint32_t)(((c - 2) >> 1) & 1));
+            tc_fence_after();
+        }
+        issue_loads(c + 2);
+        cp_async_wait<2>();  // this thread's pieces of chunk c have landed
+        unsigned char* ra = smem + LlSmem::kRaw + (c & 3) * 2 * LlSmem::kTile;
+        unsigned char* rb = same ? ra : ra + LlSmem::kTile;
+        unsigned char* la = smem + LlSmem::kLo + (c & 1) * 2 * LlSmem::kTile;
+        unsigned char* lb = same ? la : la + LlSmem::kTile;
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int off = piece_off(it);
+            *reinterpret_cast<float4*>(la + off) = lo_of(*reinterpret_cast<const float4*>(ra + off));
+            if (!same) *reinterpret_cast<float4*>(lb + off) = lo_of(*reinterpret_cast<const float4*>(rb + off));
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (t == 0) {
+            const uint64_t dAhi = make_sw128_desc(smem_u32(ra)), dAlo = make_sw128_desc(smem_u32(la));
+            const uint64_t dBhi = make_sw128_desc(smem_u32(rb)), dBlo = make_sw128_desc(smem_u32(lb));
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+                const uint32_t first = (c == 0 && kk == 0) ? 0u : 1u;
+                umma_tf32(tmem_d, dAlo + adv, dBhi + adv, kIdescTf32, first);
+                umma_tf32(tmem_d, dAhi + adv, dBlo + adv, kIdescTf32, 1u);
+                umma_tf32(tmem_d, dAhi + adv, dBhi + adv, kIdescTf32, 1u);
+            }
+            umma_commit(&bars[c & 1]);
+        }
+    }
+    // the C tile (from A) is fetched while the last chunks are still being multiplied
+    const long coff = (long)r * NB * n + (long)q * NB;
+    float4 cv[16];
+#pragma unroll
+    for (int rr = 0; rr < 16; rr++) cv[rr] = *(reinterpret_cast<const float4*>(Sb + coff + (long)(warp * 16 + rr) * n) + lane);
+    // drain the last two chunks
+    mbar_wait(&bars[(C - 2) & 1], (uint32_t)(((C - 2) >> 1) & 1));
+    mbar_wait(&bars[(C - 1) & 1], (uint32_t)(((C - 1) >> 1) & 1));
+    tc_fence_after();
+    cp_async_wait<0>();
+    {
+        float* stage = reinterpret_cast<float*>(smem);
+        const int drow = (warp & 3) * 32 + lane;
+        const int dcol0 = (warp >> 2) * 64;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            float acc[32];
+            const int col = dcol0 + h * 32;
+            tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col, acc);
+#pragma unroll
+            for (int qq = 0; qq < 8; qq++) {
+                const int c4 = (col >> 2) + qq;
+                *reinterpret_cast<float4*>(stage + drow * 128 + ((c4 ^ (drow & 7)) << 2)) =
+                    make_float4(acc[4 * qq], acc[4 * qq + 1], acc[4 * qq + 2], acc[4 * qq + 3]);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < 16; rr++) {
+            const int row = warp * 16 + rr;
+            const float4 d = *reinterpret_cast<const float4*>(stage + row * 128 + ((lane ^ (row & 7)) << 2));
+            float4 v = cv[rr];
+            v.x -= d.x, v.y -= d.y, v.z -= d.z, v.w -= d.w;
+            *(reinterpret_cast<float4*>(Lb + coff + (long)row * n) + lane) = v;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, 128);
+}
+
+// left-looking driver: per block column q: update (if q > 0), diagonal block, TRSM
+static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int n, long batch, cudaStream_t st) {
+    cudaFuncSetAttribute(blk_mma_kernel<MMA_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
+    cudaFuncSetAttribute(blk_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LlSmem::kTotal);
+    const int panels = n / NB;
+    const unsigned nb = (unsigned)batch;
+    blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, nb), 256, 0, st>>>(L, n);
+    count_launch();
+    for (int q = 0; q < panels; q++) {
+        const int o = q * NB;
+        const int mt = panels - q - 1;
+        const float* src = (q == 0) ? A : L;  // where block column q currently lives
+        if (q > 0) {
+            blk_ll_kernel<<<dim3(panels - q, nb), 256, LlSmem::kTotal, st>>>(A, L, n, q);
+            count_launch();
+        }
+        blk_diag_kernel<<<nb, 512, 0, st>>>(src, L, W, n, o);
+        count_launch();
+        if (mt > 0) {
+            blk_mma_kernel<MMA_TRSM><<<dim3(mt, nb), 256, MmaSmem::kTotal, st>>>(src, L, W, n, o);
+            count_launch();
+        }
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int use_tensor, cudaStream_t st) {
     if (n % NB != 0 || n < 2 * NB || !use_tensor) return cudaErrorNotSupported;
     if ((((uintptr_t)A | (uintptr_t)L) & 15) != 0) return cudaErrorNotSupported;
@@ -432,6 +601,16 @@ cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int us
     if ((e = cudaMallocAsync(&W, sizeof(float) * (size_t)batch * NB * NB, st)) != cudaSuccess) return e;
     cudaFuncSetAttribute(blk_mma_kernel<MMA_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
     cudaFuncSetAttribute(blk_mma_kernel<MMA_SYRK>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
+    static int right_looking = -1;  // HLSD_CHOL_RIGHT_LOOKING=1 (environment): the per-panel SYRK variant
+    if (right_looking < 0) {
+        const char* ev = getenv("HLSD_CHOL_RIGHT_LOOKING");
+        right_looking = ev ? atoi(ev) : 0;
+    }
+    if (!right_looking) {
+        e = cholesky_left_looking(A, L, W, n, batch, st);
+        cudaFreeAsync(W, st);
+        return e;
+    }
     const int panels = n / NB;
     blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, (unsigned)batch), 256, 0, st>>>(L, n);
     count_launch();
@@ -492,7 +671,8 @@ template <int SUB>
 __global__ void __launch_bounds__(256, MmaSmem::kStages == 1 ? 3 : 2)
 gemm_tile_kernel(TileArgs g) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the address space: LDS/STS, not generic LD/ST)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + MmaSmem::kBar);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + MmaSmem::kTmemPtr);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
