@@ -37,6 +37,7 @@
 namespace hlsd {
 
 constexpr int NB = 128;  // panel width = MMA tile edge
+constexpr int kDiagSmem = NB * (NB + 1) * 4;  // dynamic shared memory of blk_diag_kernel
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 / TMEM wrappers
@@ -128,104 +129,103 @@ blk_zero_upper_kernel(float* __restrict__ L, int n) {
 
 // ------------------------------------------------------------------------------------------------
 // diagonal block: L11 = chol(A11) (128 x 128, right-looking) and W = inv(L11), fused in one sweep.
-// One CTA of 512 threads per matrix; warp `tr` (16 warps) owns rows i = tr + 16 a (a < 8), lane
-// `tc` owns columns j = tc + 32 b (b < 4): an 8 x 4 register tile, dealt cyclically so that the
-// shrinking active region stays balanced.  Column j of the tile holds A[:, j] while k < j and, once
-// column j has been finished (k >= j), W[:, j]: the two rank-1 updates of step k
+// One CTA of 512 threads per matrix.  Warp w (16 warps) owns COLUMNS j = w + 16 b (b < 8), lane l owns
+// ROWS i = l + 32 a (a < 4): a 4 x 8 register tile per thread, dealt cyclically so that the shrinking
+// active region stays balanced.  Column j of the tile holds A[:, j] while k < j and, once column j has
+// been finished (k >= j), W[:, j]: the two rank-1 updates of step k
 //      A[i][j] -= l_ik * l_jk   (i > k, j > k)          W[i][j] -= l_ik * w_kj   (i > k, j <= k)
-// touch disjoint columns, so one register tile and one broadcast vector u (u[j] = l_jk for j > k,
-// w_kj for j <= k) serve both.  W follows from forward substitution on the identity:
-// W[k][:] = (e_k - sum_{j<k} l_kj W[j][:]) / l_kk.  Per step: the owners of column k scale it,
-// publish it (the systolic "column stream"), store it to L and re-seed the registers with e_k; the
-// owners of row k of W scale and publish it; everyone applies the update; the owner of (k+1, k+1)
-// takes the next square root.  Plain fp32 FMA arithmetic (tensor path: tolerance-checked).
+// touch disjoint columns, so one register tile serves both (W follows from forward substitution on
+// the identity: W[k][:] = (e_k - sum_{j<k} l_kj W[j][:]) / l_kk).  With whole columns inside one warp:
+//   * column k is scaled and published (the systolic "column stream") by ONE warp with all lanes busy;
+//   * the diagonal element that the next step needs sits in that same warp: the next pivot root is
+//     taken there and travels with the column through shared memory, so there is ONE barrier per step
+//     (publication buffers double-buffered by the parity of k);
+//   * row k of W, which every column needs as multiplier w_kj, sits in lane k % 32 of the very warp
+//     that owns column j: a shuffle, no shared memory and no divergent single-lane section.
+// L11 is collected in a shared-memory tile and written out row-wise at the end.
+// Plain fp32 FMA arithmetic (tensor path: tolerance-checked).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512, 2)
 blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __restrict__ W, int n, int o) {
-    __shared__ float ubuf[NB];
-    __shared__ float sdiag;
-    const int tr = threadIdx.x >> 5, tc = threadIdx.x & 31;
+    extern __shared__ __align__(16) float dg_tile[];  // [NB][NB + 1]
+    __shared__ float ubuf[2][NB];                     // ubuf[k & 1][i] = l_ik for i > k
+    __shared__ float sdiag[2];                        // sdiag[k & 1] = l_kk
+    constexpr int ld = NB + 1;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     float* blk = L + (long)blockIdx.x * n * n + (long)o * n + o;
     const float* sblk = S + (long)blockIdx.x * n * n + (long)o * n + o;  // S = A for panel 0, L afterwards
-    float v[8][4];
-#pragma unroll
-    for (int ia = 0; ia < 8; ia++)
-#pragma unroll
-        for (int ib = 0; ib < 4; ib++) {
-            const int i = tr + 16 * ia, j = tc + 32 * ib;
-            v[ia][ib] = (j <= i) ? sblk[(long)i * n + j] : 0.0f;
-        }
-    if (threadIdx.x == 0) sdiag = sqrtf(v[0][0]);
+    for (int e = threadIdx.x; e < NB * NB; e += 512) {
+        const int i = e >> 7, j = e & (NB - 1);
+        dg_tile[i * ld + j] = (j <= i) ? sblk[(long)i * n + j] : 0.0f;
+    }
     __syncthreads();
-    // k = 16 * KA + kr with KA compile-time: the register that holds row/column k is then a constant
-    // index (a runtime index would push the tile into local memory)
-    static_for<0, 8>([&](auto kac) {
-        constexpr int KA = decltype(kac)::value;  // local row of row k
-        constexpr int KB = KA >> 1;               // local column of column k
+    float v[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) v[a][b] = dg_tile[(l + 32 * a) * ld + w + 16 * b];
+    __syncthreads();  // the tile is rebuilt as L11 below
+    // k = 16 * BK + kr with BK compile-time, so that the registers of column k / row k have constant indices
+    static_for<0, 8>([&](auto bkc) {
+        constexpr int BK = decltype(bkc)::value;  // column slot of column k
+        constexpr int AK = BK >> 1;               // row slot of row k
         for (int kr = 0; kr < 16; kr++) {
-            const int k = 16 * KA + kr;
-            const int kc = k & 31;
-            const float d = sdiag;
-            const float rd = 1.0f / d;
-            if (tc == kc) {  // column k: scale, publish, store, re-seed with column k of the identity
+            const int k = 16 * BK + kr;
+            const int lk = k & 31;
+            float* ub = ubuf[k & 1];
+            if (w == kr) {  // this warp owns column k (all rows): root, scale, publish, re-seed with e_k
+                const float d = sqrtf(__shfl_sync(0xffffffffu, v[AK][BK], lk));
+                const float rd = 1.0f / d;
+                if (l == 0) sdiag[k & 1] = d;
 #pragma unroll
-                for (int ia = 0; ia < 8; ia++) {
-                    const int i = tr + 16 * ia;
-                    if (i > k) {
-                        const float l = v[ia][KB] * rd;
-                        ubuf[i] = l;
-                        blk[(long)i * n + k] = l;
-                        v[ia][KB] = 0.0f;
-                    } else if (i == k) {
-                        blk[(long)i * n + k] = d;
-                        v[ia][KB] = 1.0f;
-                    } else {
-                        blk[(long)i * n + k] = 0.0f;  // above the diagonal (SYRK left scratch there)
-                        v[ia][KB] = 0.0f;
-                    }
-                }
-            }
-            if (tr == kr) {  // row k of W (columns <= k): scale and publish
-#pragma unroll
-                for (int ib = 0; ib < 4; ib++) {
-                    const int j = tc + 32 * ib;
-                    if (j <= k) {
-                        v[KA][ib] *= rd;
-                        ubuf[j] = v[KA][ib];
-                    }
+                for (int a = 0; a < 4; a++) {
+                    const int i = l + 32 * a;
+                    const float lv = v[a][BK] * rd;
+                    if (i > k) ub[i] = lv;
+                    dg_tile[i * ld + k] = (i > k) ? lv : (i == k ? d : 0.0f);
+                    v[a][BK] = (i == k) ? 1.0f : 0.0f;
                 }
             }
             __syncthreads();
-            float u[4];
+            const float rd = 1.0f / sdiag[k & 1];
+            float u[8];
 #pragma unroll
-            for (int ib = 0; ib < 4; ib++) u[ib] = ubuf[tc + 32 * ib];
-            static_for<KA, 8>([&](auto iac) {  // rows i = tr + 16 ia <= k for ia < KA: nothing to do
-                constexpr int ia = decltype(iac)::value;
-                const int i = tr + 16 * ia;
-                if (i > k) {  // warp-uniform
-                    const float lr = ubuf[i];
-                    // columns j = tc + 32 ib > i are never needed (both L11 and W are lower triangular):
-                    // i <= 16 ia + 15, so only the slots ib <= ia / 2 can hold j <= i
-#pragma unroll
-                    for (int ib = 0; ib <= ia / 2; ib++) v[ia][ib] = fmaf(-lr, u[ib], v[ia][ib]);
+            for (int b = 0; b < 8; b++) {
+                const int j = w + 16 * b;  // warp-uniform
+                if (j > k) {
+                    u[b] = ub[j];  // l_jk
+                } else {
+                    u[b] = __shfl_sync(0xffffffffu, v[AK][b], lk) * rd;  // w_kj, from the row-k lane of this warp
+                    if (l == lk) v[AK][b] = u[b];                        // row k of W is final
                 }
+            }
+            static_for<AK, 4>([&](auto ac) {  // row slots below AK hold rows <= k only
+                constexpr int a = decltype(ac)::value;
+                const int i = l + 32 * a;
+                const float lr = (i > k) ? ub[i] : 0.0f;
+                // columns j = w + 16 b > i are never needed: i <= 32 a + 31, so b <= 2 a + 1 suffices
+#pragma unroll
+                for (int b = 0; b <= 2 * a + 1; b++) v[a][b] = fmaf(-lr, u[b], v[a][b]);
             });
-            // the owner of (k+1, k+1) holds its final value now: take the next square root
-            if (k + 1 < NB && tr == ((k + 1) & 15) && tc == ((k + 1) & 31)) {
-                constexpr int KA1 = KA + 1 < 8 ? KA + 1 : 7;
-                sdiag = sqrtf(kr < 15 ? v[KA][KB] : v[KA1][KA1 >> 1]);
-            }
-            __syncthreads();
         }
     });
+    __syncthreads();
+    // L11 rows (zeros above the diagonal), then W through the same tile
+    for (int e = threadIdx.x; e < NB * NB; e += 512) {
+        const int i = e >> 7, j = e & (NB - 1);
+        blk[(long)i * n + j] = (j <= i) ? dg_tile[i * ld + j] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) dg_tile[(l + 32 * a) * ld + w + 16 * b] = v[a][b];
+    __syncthreads();
     float* wout = W + (long)blockIdx.x * NB * NB;
-#pragma unroll
-    for (int ia = 0; ia < 8; ia++)
-#pragma unroll
-        for (int ib = 0; ib < 4; ib++) {
-            const int i = tr + 16 * ia, j = tc + 32 * ib;
-            wout[i * NB + j] = (j <= i) ? v[ia][ib] : 0.0f;
-        }
+    for (int e = threadIdx.x; e < NB * NB; e += 512) {
+        const int i = e >> 7, j = e & (NB - 1);
+        wout[e] = (j <= i) ? dg_tile[i * ld + j] : 0.0f;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -568,6 +568,7 @@ blk_ll_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) 
 static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int n, long batch, cudaStream_t st) {
     cudaFuncSetAttribute(blk_mma_kernel<MMA_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
     cudaFuncSetAttribute(blk_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LlSmem::kTotal);
+    cudaFuncSetAttribute(blk_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
     const int panels = n / NB;
     const unsigned nb = (unsigned)batch;
     blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, nb), 256, 0, st>>>(L, n);
@@ -580,7 +581,7 @@ static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int
             blk_ll_kernel<<<dim3(panels - q, nb), 256, LlSmem::kTotal, st>>>(A, L, n, q);
             count_launch();
         }
-        blk_diag_kernel<<<nb, 512, 0, st>>>(src, L, W, n, o);
+        blk_diag_kernel<<<nb, 512, kDiagSmem, st>>>(src, L, W, n, o);
         count_launch();
         if (mt > 0) {
             blk_mma_kernel<MMA_TRSM><<<dim3(mt, nb), 256, MmaSmem::kTotal, st>>>(src, L, W, n, o);
@@ -601,6 +602,7 @@ cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int us
     if ((e = cudaMallocAsync(&W, sizeof(float) * (size_t)batch * NB * NB, st)) != cudaSuccess) return e;
     cudaFuncSetAttribute(blk_mma_kernel<MMA_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
     cudaFuncSetAttribute(blk_mma_kernel<MMA_SYRK>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
+    cudaFuncSetAttribute(blk_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
     static int right_looking = -1;  // HLSD_CHOL_RIGHT_LOOKING=1 (environment): the per-panel SYRK variant
     if (right_looking < 0) {
         const char* ev = getenv("HLSD_CHOL_RIGHT_LOOKING");
@@ -618,7 +620,7 @@ cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int us
         const int o = p * NB;
         const int mt = panels - p - 1;  // 128-row blocks below the diagonal block
         const float* src = (p == 0) ? A : L;
-        blk_diag_kernel<<<(unsigned)batch, 512, 0, st>>>(src, L, W, n, o);
+        blk_diag_kernel<<<(unsigned)batch, 512, kDiagSmem, st>>>(src, L, W, n, o);
         count_launch();
         if (mt > 0) {
             blk_mma_kernel<MMA_TRSM><<<dim3(mt, (unsigned)batch), 256, MmaSmem::kTotal, st>>>(src, L, W, n, o);
