@@ -188,21 +188,36 @@ blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __res
             }
             __syncthreads();
             const float rd = 1.0f / sdiag[k & 1];
+            // multipliers per column slot: slots b < BK hold columns j < 16 BK <= k (finished: w_kj, shuffled from
+            // the row-k lane of this warp), slots b > BK hold columns j > k (l_jk from the column stream);
+            // only slot BK needs a run-time test (j = w + 16 BK <= k  <=>  w <= kr)
             float u[8];
-#pragma unroll
-            for (int b = 0; b < 8; b++) {
-                const int j = w + 16 * b;  // warp-uniform
-                if (j > k) {
-                    u[b] = ub[j];  // l_jk
+            static_for<0, 8>([&](auto bc) {
+                constexpr int b = decltype(bc)::value;
+                if constexpr (b < BK) {
+                    u[b] = __shfl_sync(0xffffffffu, v[AK][b], lk) * rd;
+                    if (l == lk) v[AK][b] = u[b];  // row k of W is final
+                } else if constexpr (b > BK) {
+                    u[b] = ub[w + 16 * b];
                 } else {
-                    u[b] = __shfl_sync(0xffffffffu, v[AK][b], lk) * rd;  // w_kj, from the row-k lane of this warp
-                    if (l == lk) v[AK][b] = u[b];                        // row k of W is final
+                    if (w <= kr) {
+                        u[b] = __shfl_sync(0xffffffffu, v[AK][b], lk) * rd;
+                        if (l == lk) v[AK][b] = u[b];
+                    } else {
+                        u[b] = ub[w + 16 * b];
+                    }
                 }
-            }
-            static_for<AK, 4>([&](auto ac) {  // row slots below AK hold rows <= k only
-                constexpr int a = decltype(ac)::value;
-                const int i = l + 32 * a;
+            });
+            // row slot AK may still hold rows <= k (run-time test); slots above it hold rows > k only
+            {
+                const int i = l + 32 * AK;
                 const float lr = (i > k) ? ub[i] : 0.0f;
+#pragma unroll
+                for (int b = 0; b <= 2 * AK + 1; b++) v[AK][b] = fmaf(-lr, u[b], v[AK][b]);
+            }
+            static_for<AK + 1, 4>([&](auto ac) {
+                constexpr int a = decltype(ac)::value;
+                const float lr = ub[l + 32 * a];
                 // columns j = w + 16 b > i are never needed: i <= 32 a + 31, so b <= 2 a + 1 suffices
 #pragma unroll
                 for (int b = 0; b <= 2 * a + 1; b++) v[a][b] = fmaf(-lr, u[b], v[a][b]);
