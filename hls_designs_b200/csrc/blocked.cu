@@ -145,6 +145,9 @@ blk_zero_upper_kernel(float* __restrict__ L, int n) {
 // L11 is collected in a shared-memory tile and written out row-wise at the end.
 // Plain fp32 FMA arithmetic (tensor path: tolerance-checked).
 // ------------------------------------------------------------------------------------------------
+// INV_ONLY: the block at S is an already finished UNIT lower triangular factor (blocked LU): only W = inv(L11)
+// is produced (no roots, no scaling, the unfinished-column updates are switched off, L is not written).
+template <bool INV_ONLY>
 __global__ void __launch_bounds__(512, 2)
 blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __restrict__ W, int n, int o) {
     extern __shared__ __align__(16) float dg_tile[];  // [NB][NB + 1]
@@ -174,8 +177,8 @@ blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __res
             const int lk = k & 31;
             float* ub = ubuf[k & 1];
             if (w == kr) {  // this warp owns column k (all rows): root, scale, publish, re-seed with e_k
-                const float d = sqrtf(__shfl_sync(0xffffffffu, v[AK][BK], lk));
-                const float rd = 1.0f / d;
+                const float d = INV_ONLY ? 1.0f : sqrtf(__shfl_sync(0xffffffffu, v[AK][BK], lk));
+                const float rd = INV_ONLY ? 1.0f : 1.0f / d;
                 if (l == 0) sdiag[k & 1] = d;
 #pragma unroll
                 for (int a = 0; a < 4; a++) {
@@ -187,7 +190,7 @@ blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __res
                 }
             }
             __syncthreads();
-            const float rd = 1.0f / sdiag[k & 1];
+            const float rd = INV_ONLY ? 1.0f : 1.0f / sdiag[k & 1];
             // multipliers per column slot: slots b < BK hold columns j < 16 BK <= k (finished: w_kj, shuffled from
             // the row-k lane of this warp), slots b > BK hold columns j > k (l_jk from the column stream);
             // only slot BK needs a run-time test (j = w + 16 BK <= k  <=>  w <= kr)
@@ -198,13 +201,13 @@ blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __res
                     u[b] = __shfl_sync(0xffffffffu, v[AK][b], lk) * rd;
                     if (l == lk) v[AK][b] = u[b];  // row k of W is final
                 } else if constexpr (b > BK) {
-                    u[b] = ub[w + 16 * b];
+                    u[b] = INV_ONLY ? 0.0f : ub[w + 16 * b];
                 } else {
                     if (w <= kr) {
                         u[b] = __shfl_sync(0xffffffffu, v[AK][b], lk) * rd;
                         if (l == lk) v[AK][b] = u[b];
                     } else {
-                        u[b] = ub[w + 16 * b];
+                        u[b] = INV_ONLY ? 0.0f : ub[w + 16 * b];
                     }
                 }
             });
@@ -226,10 +229,11 @@ blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __res
     });
     __syncthreads();
     // L11 rows (zeros above the diagonal), then W through the same tile
-    for (int e = threadIdx.x; e < NB * NB; e += 512) {
-        const int i = e >> 7, j = e & (NB - 1);
-        blk[(long)i * n + j] = (j <= i) ? dg_tile[i * ld + j] : 0.0f;
-    }
+    if (!INV_ONLY)
+        for (int e = threadIdx.x; e < NB * NB; e += 512) {
+            const int i = e >> 7, j = e & (NB - 1);
+            blk[(long)i * n + j] = (j <= i) ? dg_tile[i * ld + j] : 0.0f;
+        }
     __syncthreads();
 #pragma unroll
     for (int a = 0; a < 4; a++)
@@ -583,7 +587,7 @@ blk_ll_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) 
 static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int n, long batch, cudaStream_t st) {
     cudaFuncSetAttribute(blk_mma_kernel<MMA_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
     cudaFuncSetAttribute(blk_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LlSmem::kTotal);
-    cudaFuncSetAttribute(blk_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
+    cudaFuncSetAttribute(blk_diag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
     const int panels = n / NB;
     const unsigned nb = (unsigned)batch;
     blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, nb), 256, 0, st>>>(L, n);
@@ -596,7 +600,7 @@ static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int
             blk_ll_kernel<<<dim3(panels - q, nb), 256, LlSmem::kTotal, st>>>(A, L, n, q);
             count_launch();
         }
-        blk_diag_kernel<<<nb, 512, kDiagSmem, st>>>(src, L, W, n, o);
+        blk_diag_kernel<false><<<nb, 512, kDiagSmem, st>>>(src, L, W, n, o);
         count_launch();
         if (mt > 0) {
             blk_mma_kernel<MMA_TRSM><<<dim3(mt, nb), 256, MmaSmem::kTotal, st>>>(src, L, W, n, o);
@@ -617,7 +621,7 @@ cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int us
     if ((e = cudaMallocAsync(&W, sizeof(float) * (size_t)batch * NB * NB, st)) != cudaSuccess) return e;
     cudaFuncSetAttribute(blk_mma_kernel<MMA_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
     cudaFuncSetAttribute(blk_mma_kernel<MMA_SYRK>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
-    cudaFuncSetAttribute(blk_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
+    cudaFuncSetAttribute(blk_diag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
     static int right_looking = -1;  // HLSD_CHOL_RIGHT_LOOKING=1 (environment): the per-panel SYRK variant
     if (right_looking < 0) {
         const char* ev = getenv("HLSD_CHOL_RIGHT_LOOKING");
@@ -635,7 +639,7 @@ cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int us
         const int o = p * NB;
         const int mt = panels - p - 1;  // 128-row blocks below the diagonal block
         const float* src = (p == 0) ? A : L;
-        blk_diag_kernel<<<(unsigned)batch, 512, kDiagSmem, st>>>(src, L, W, n, o);
+        blk_diag_kernel<false><<<(unsigned)batch, 512, kDiagSmem, st>>>(src, L, W, n, o);
         count_launch();
         if (mt > 0) {
             blk_mma_kernel<MMA_TRSM><<<dim3(mt, (unsigned)batch), 256, MmaSmem::kTotal, st>>>(src, L, W, n, o);
@@ -666,7 +670,7 @@ cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int us
 //                          need L in final row order); once L21 has served as operand, the panel's L
 //                          columns go back to the reference's convention (multipliers stay where they
 //                          were computed); exchanges of later panels never touch them
-//     3. lu_inv_kernel     (SIMT) W = inv(L11), unit lower triangular
+//     3. blk_diag_kernel<INV_ONLY> (SIMT) W = inv(L11), unit lower triangular
 //     4. lu_gather_kernel  (SIMT) T0 = A12^T  (k contiguous: the tensor core wants K-major operands)
 //     5. gemm_tile_kernel<0> (tcgen05) T1 = T0 * W^T = U12^T
 //     6. lu_scatter_kernel (SIMT) U12 = T1^T back into the working matrix
@@ -975,18 +979,19 @@ lu_panel_kernel(float* __restrict__ Wk, float* __restrict__ L, int* __restrict__
 
 // Slots of the rows a panel's 128 exchanges touch: slots 0..127 are positions o..o+127, further slots are
 // the distinct pivot rows below the panel.  pslot[kk] = slot of P[o + kk].  Returns the slot count.
-__device__ __forceinline__ int lu_touched_rows(const int* piv, int o, int* pos, int* pslot) {
+// `slotmap` (n ints of shared memory, set to -1 by the caller) maps a row below the panel to its slot.
+__device__ __forceinline__ int lu_touched_rows(const int* piv, int o, int* pos, int* pslot, int* slotmap) {
     int cnt = NB;
     for (int kk = 0; kk < NB; kk++) pos[kk] = o + kk;
     for (int kk = 0; kk < NB; kk++) {
         const int p = piv[kk];
-        int sp = -1;
+        int sp;
         if (p < o + NB) sp = p - o;
         else {
-            for (int q = NB; q < cnt; q++)
-                if (pos[q] == p) sp = q;
+            sp = slotmap[p];
             if (sp < 0) {
                 sp = cnt;
+                slotmap[p] = cnt;
                 pos[cnt++] = p;
             }
         }
@@ -1001,12 +1006,14 @@ __device__ __forceinline__ int lu_touched_rows(const int* piv, int o, int* pos, 
 // exchange steps.  grid: (ceil(ncols / 128), batch), 128 threads
 __global__ void __launch_bounds__(128)
 lu_swap_kernel(float* __restrict__ Wk, const int* __restrict__ P, int n, int o) {
+    extern __shared__ int slotmap[];  // n ints
     __shared__ int piv[NB], pos[2 * NB], pslot[NB], src[2 * NB];
     __shared__ int ntouch;
     piv[threadIdx.x] = P[(long)blockIdx.y * n + o + threadIdx.x];
+    for (int i = threadIdx.x; i < n; i += 128) slotmap[i] = -1;
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int cnt = lu_touched_rows(piv, o, pos, pslot);
+        const int cnt = lu_touched_rows(piv, o, pos, pslot, slotmap);
         for (int q = 0; q < cnt; q++) src[q] = q;
         for (int kk = 0; kk < NB; kk++) {
             const int sp = pslot[kk], tmp = src[kk];
@@ -1034,13 +1041,15 @@ lu_swap_kernel(float* __restrict__ Wk, const int* __restrict__ P, int n, int o) 
 // (<= 256) x 128 columns are staged in shared memory.  grid: (batch), 256 threads
 __global__ void __launch_bounds__(256)
 lu_unswap_panel_kernel(float* __restrict__ L, const int* __restrict__ P, int n, int o) {
-    extern __shared__ __align__(16) float us_tile[];  // [2 * NB][NB + 1]
+    extern __shared__ __align__(16) float us_tile[];  // [2 * NB][NB + 1] floats, then n ints (slot map)
     __shared__ int piv[NB], pos[2 * NB], pslot[NB];
     __shared__ int ntouch;
     constexpr int ld = NB + 1;
+    int* slotmap = reinterpret_cast<int*>(us_tile + 2 * NB * ld);
     if (threadIdx.x < NB) piv[threadIdx.x] = P[(long)blockIdx.x * n + o + threadIdx.x];
+    for (int i = threadIdx.x; i < n; i += 256) slotmap[i] = -1;
     __syncthreads();
-    if (threadIdx.x == 0) ntouch = lu_touched_rows(piv, o, pos, pslot);
+    if (threadIdx.x == 0) ntouch = lu_touched_rows(piv, o, pos, pslot, slotmap);
     __syncthreads();
     const int cnt = ntouch;
     float* base = L + (long)blockIdx.x * n * n + o;
@@ -1064,35 +1073,6 @@ lu_unswap_panel_kernel(float* __restrict__ L, const int* __restrict__ P, int n, 
     for (int e = threadIdx.x; e < cnt * NB; e += 256) {
         const int q = e >> 7, c = e & (NB - 1);
         base[(long)pos[q] * n + c] = us_tile[q * ld + c];
-    }
-}
-
-// W = inv(L11), L11 unit lower triangular 128 x 128 (from the L buffer); one CTA of 128 threads per matrix
-__global__ void __launch_bounds__(128)
-lu_inv_kernel(const float* __restrict__ L, float* __restrict__ W, int n, int o) {
-    extern __shared__ __align__(16) float smem_f[];
-    constexpr int ld = NB + 1;
-    float* l = smem_f;
-    float* x = smem_f + NB * ld;
-    const int t = threadIdx.x;
-    const float* blk = L + (long)blockIdx.x * n * n + (long)o * n + o;
-    for (int e = t; e < NB * NB; e += 128) {
-        const int i = e / NB, j = e - i * NB;
-        l[i * ld + j] = blk[(long)i * n + j];
-    }
-    __syncthreads();
-    const int c = t;  // column c of the inverse by forward substitution
-    for (int i = 0; i < NB; i++) {
-        float s = (i == c) ? 1.0f : 0.0f;
-        if (i > c)
-            for (int k = c; k < i; k++) s = fmaf(-l[i * ld + k], x[k * ld + c], s);
-        x[i * ld + c] = (i >= c) ? s : 0.0f;
-    }
-    __syncthreads();
-    float* wout = W + (long)blockIdx.x * NB * NB;
-    for (int e = t; e < NB * NB; e += 128) {
-        const int i = e / NB, j = e - i * NB;
-        wout[e] = x[i * ld + j];
     }
 }
 
@@ -1127,10 +1107,9 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
     if ((e = cudaMallocAsync(&Winv, sizeof(float) * (size_t)batch * NB * NB, st)) != cudaSuccess) return e;
     if ((e = cudaMallocAsync(&T0, sizeof(float) * (size_t)batch * n * NB, st)) != cudaSuccess) return e;
     if ((e = cudaMallocAsync(&T1, sizeof(float) * (size_t)batch * n * NB, st)) != cudaSuccess) return e;
-    const size_t inv_smem = 2 * NB * (NB + 1) * sizeof(float);
-    const size_t unswap_smem = (size_t)2 * NB * (NB + 1) * sizeof(float);
+    const size_t unswap_smem = (size_t)2 * NB * (NB + 1) * sizeof(float) + (size_t)n * sizeof(int);
     cudaFuncSetAttribute(lu_unswap_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)unswap_smem);
-    cudaFuncSetAttribute(lu_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem);
+    cudaFuncSetAttribute(blk_diag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
     cudaFuncSetAttribute(gemm_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
     cudaFuncSetAttribute(gemm_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
     const unsigned nb = (unsigned)batch;
@@ -1150,9 +1129,9 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
             count_launch();
             break;
         }
-        lu_swap_kernel<<<dim3((ncols + 127) / 128, nb), 128, 0, st>>>(U, P, n, o);
+        lu_swap_kernel<<<dim3((ncols + 127) / 128, nb), 128, n * sizeof(int), st>>>(U, P, n, o);
         count_launch();
-        lu_inv_kernel<<<nb, 128, inv_smem, st>>>(L, Winv, n, o);
+        blk_diag_kernel<true><<<nb, 512, kDiagSmem, st>>>(L, L, Winv, n, o);  // W = inv(L11), L11 unit lower
         count_launch();
         lu_transpose_kernel<0><<<dim3(ncols / 32, 4, nb), dim3(32, 8), 0, st>>>(U, T0, n, o);
         count_launch();
