@@ -314,14 +314,16 @@ def main():
     gflops = flops(kind, rows, cols) * batch / (med_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "traffic": traffic if batch == WORKLOADS[args.workload][3] else None, "peak_source": peak_src,
-                "kernel_ms_median": med_ms, "algorithmic_bytes_per_launch": bytes_per_launch, "gflops": gflops}
+                "kernel_ms_median": med_ms, "kernel_ms_min": min(kern_ms), "kernel_ms_max": max(kern_ms),
+                "algorithmic_bytes_per_launch": bytes_per_launch, "gflops": gflops}
     if kind in ("chol", "lu") and rows >= 256:
         # blocked tensor-core path: the step is ~25 launches; the dominant kernel (the tcgen05 tile kernel) does the
         # useful flops (N^3/3 Cholesky, 2N^3/3 LU) three times (3xTF32).  Peak: tf32 dense = half the measured bf16 rate.
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
         ach = gflops / 1e3
         roofline = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                    "traffic": None, "kernel_ms_median": med_ms, "gflops": gflops,
+                    "traffic": None, "kernel_ms_median": med_ms, "kernel_ms_min": min(kern_ms),
+                    "kernel_ms_max": max(kern_ms), "gflops": gflops,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 runs at half the bf16 rate)",
                     "note": "achieved = useful flops of the whole step (N^3/3 Cholesky, 2N^3/3 LU) / step time; the tensor "
                             "pipe executes 3x that (3xTF32); a step is one launch per panel and stage, see profiles/"}

@@ -611,7 +611,22 @@ static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// The workspaces come from the stream-ordered allocator; keep what it has reserved between calls
+// (the default pool hands memory back to the driver at every synchronisation point).
+static void keep_pool_memory() {
+    static thread_local int done_for = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done_for = dev;
+}
+
 cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int use_tensor, cudaStream_t st) {
+    keep_pool_memory();
     if (n % NB != 0 || n < 2 * NB || !use_tensor) return cudaErrorNotSupported;
     if ((((uintptr_t)A | (uintptr_t)L) & 15) != 0) return cudaErrorNotSupported;
     if (batch == 0) return cudaSuccess;
@@ -1102,6 +1117,7 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
     if ((((uintptr_t)A | (uintptr_t)L | (uintptr_t)U) & 15) != 0) return cudaErrorNotSupported;
     if (batch == 0) return cudaSuccess;
     if (batch > 65535) return cudaErrorNotSupported;
+    keep_pool_memory();
     cudaError_t e;
     float *Winv = nullptr, *T0 = nullptr, *T1 = nullptr;
     if ((e = cudaMallocAsync(&Winv, sizeof(float) * (size_t)batch * NB * NB, st)) != cudaSuccess) return e;
