@@ -461,7 +461,9 @@ struct LlSmem {
     static constexpr int kTotal = kBar + 32 + 1024;
 };
 
-__global__ void __launch_bounds__(256, 1)
+constexpr int kLlThreads = 512;  // 16 warps: two 16-byte pieces per operand, chunk and thread
+
+__global__ void __launch_bounds__(kLlThreads, 1)
 blk_ll_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) {
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the address space: LDS/STS, not generic LD/ST)
@@ -488,8 +490,9 @@ blk_ll_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) 
     tc_fence_after();
     const uint32_t tmem_d = *tmem_ptr;
 
+    constexpr int kPieces = 1024 / kLlThreads;  // 16-byte pieces per operand, chunk and thread
     auto piece_off = [&](int it) {
-        const int idx = it * 256 + t, row = idx >> 3, c4 = idx & 7;
+        const int idx = it * kLlThreads + t, row = idx >> 3, c4 = idx & 7;
         return row * 128 + ((c4 ^ (row & 7)) << 4);
     };
     auto issue_loads = [&](int c) {
@@ -497,8 +500,8 @@ blk_ll_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) 
             unsigned char* ra = smem + LlSmem::kRaw + (c & 3) * 2 * LlSmem::kTile;
             unsigned char* rb = ra + LlSmem::kTile;
 #pragma unroll
-            for (int it = 0; it < 4; it++) {
-                const int idx = it * 256 + t, row = idx >> 3, c4 = idx & 7;
+            for (int it = 0; it < kPieces; it++) {
+                const int idx = it * kLlThreads + t, row = idx >> 3, c4 = idx & 7;
                 cp_async16(ra + piece_off(it), Arows + (long)row * n + c * 32 + c4 * 4);
                 if (!same) cp_async16(rb + piece_off(it), Brows + (long)row * n + c * 32 + c4 * 4);
             }
@@ -519,7 +522,7 @@ blk_ll_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) 
         unsigned char* la = smem + LlSmem::kLo + (c & 1) * 2 * LlSmem::kTile;
         unsigned char* lb = same ? la : la + LlSmem::kTile;
 #pragma unroll
-        for (int it = 0; it < 4; it++) {
+        for (int it = 0; it < kPieces; it++) {
             const int off = piece_off(it);
             *reinterpret_cast<float4*>(la + off) = lo_of(*reinterpret_cast<const float4*>(ra + off));
             if (!same) *reinterpret_cast<float4*>(lb + off) = lo_of(*reinterpret_cast<const float4*>(rb + off));
@@ -544,9 +547,11 @@ blk_ll_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) 
     }
     // the C tile (from A) is fetched while the last chunks are still being multiplied
     const long coff = (long)r * NB * n + (long)q * NB;
-    float4 cv[16];
+    constexpr int kRowsPerWarp = 128 / (kLlThreads / 32);
+    float4 cv[kRowsPerWarp];
 #pragma unroll
-    for (int rr = 0; rr < 16; rr++) cv[rr] = *(reinterpret_cast<const float4*>(Sb + coff + (long)(warp * 16 + rr) * n) + lane);
+    for (int rr = 0; rr < kRowsPerWarp; rr++)
+        cv[rr] = *(reinterpret_cast<const float4*>(Sb + coff + (long)(warp * kRowsPerWarp + rr) * n) + lane);
     // drain the last two chunks
     mbar_wait(&bars[(C - 2) & 1], (uint32_t)(((C - 2) >> 1) & 1));
     mbar_wait(&bars[(C - 1) & 1], (uint32_t)(((C - 1) >> 1) & 1));
@@ -554,10 +559,11 @@ blk_ll_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) 
     cp_async_wait<0>();
     {
         float* stage = reinterpret_cast<float*>(smem);
-        const int drow = (warp & 3) * 32 + lane;
-        const int dcol0 = (warp >> 2) * 64;
+        const int drow = (warp & 3) * 32 + lane;  // accumulator row = TMEM lane (warp % 4 selects the lane quarter)
+        constexpr int kColsPerWarp = 128 / (kLlThreads / 128);
+        const int dcol0 = (warp >> 2) * kColsPerWarp;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
+        for (int h = 0; h < kColsPerWarp / 32; h++) {
             float acc[32];
             const int col = dcol0 + h * 32;
             tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col, acc);
@@ -570,8 +576,8 @@ blk_ll_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) 
         }
         __syncthreads();
 #pragma unroll
-        for (int rr = 0; rr < 16; rr++) {
-            const int row = warp * 16 + rr;
+        for (int rr = 0; rr < kRowsPerWarp; rr++) {
+            const int row = warp * kRowsPerWarp + rr;
             const float4 d = *reinterpret_cast<const float4*>(stage + row * 128 + ((lane ^ (row & 7)) << 2));
             float4 v = cv[rr];
             v.x -= d.x, v.y -= d.y, v.z -= d.z, v.w -= d.w;
@@ -597,7 +603,7 @@ static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int
         const int mt = panels - q - 1;
         const float* src = (q == 0) ? A : L;  // where block column q currently lives
         if (q > 0) {
-            blk_ll_kernel<<<dim3(panels - q, nb), 256, LlSmem::kTotal, st>>>(A, L, n, q);
+            blk_ll_kernel<<<dim3(panels - q, nb), kLlThreads, LlSmem::kTotal, st>>>(A, L, n, q);
             count_launch();
         }
         blk_diag_kernel<false><<<nb, 512, kDiagSmem, st>>>(src, L, W, n, o);
