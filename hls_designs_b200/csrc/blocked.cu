@@ -447,16 +447,16 @@ blk_mma_kernel(const float* __restrict__ S, float* __restrict__ L, const float* 
 // Left-looking trailing update: tile (r, q) of block column q receives ALL earlier panels at once,
 //      X[r][q] = A[r][q] - sum_{j<q} L[r][j] * L[q][j]^T         (K = 128 q, up to 896)
 // so C is read (from A) and written (to L) once per tile instead of once per panel, and the K loop is
-// long enough to pipeline: cp.async fills a ring of 4 raw stages two chunks ahead, the threads
-// produce the lo tile of chunk c while the tensor core still multiplies chunk c-1 (lo tiles double
+// long enough to pipeline: global loads run two chunks ahead in registers, the threads write the raw
+// (= hi) and lo tiles of chunk c while the tensor core still multiplies chunk c-1 (both double
 // buffered), completion of chunk c-2 (tcgen05.commit -> one of two mbarriers) frees its buffers.
-// 192 KB of shared memory, one CTA per SM.  grid: (panels - q, batch): r = q + blockIdx.x
+// 128 KB of shared memory, one CTA per SM.  grid: (panels - q, batch): r = q + blockIdx.x
 // ------------------------------------------------------------------------------------------------
 struct LlSmem {
     static constexpr int kTile = 128 * 32 * 4;                 // one operand chunk: 128 rows x 32 k
-    static constexpr int kRaw = 0;                             // [4 stages][A, B]
-    static constexpr int kLo = 8 * kTile;                      // [2][A, B]
-    static constexpr int kBar = 12 * kTile;                    // two mbarriers
+    static constexpr int kRaw = 0;                             // [2][A, B] raw fp32 = tf32 hi operands
+    static constexpr int kLo = 4 * kTile;                      // [2][A, B] lo operands
+    static constexpr int kBar = 8 * kTile;                     // two mbarriers
     static constexpr int kTmemPtr = kBar + 16;
     static constexpr int kTotal = kBar + 32 + 1024;
 };
@@ -495,38 +495,42 @@ blk_ll_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) 
         const int idx = it * kLlThreads + t, row = idx >> 3, c4 = idx & 7;
         return row * 128 + ((c4 ^ (row & 7)) << 4);
     };
-    auto issue_loads = [&](int c) {
+    // Register-staged operand stream: chunk c+2 is loaded (plain 16-byte global loads) into the register
+    // buffer that chunk c has just vacated; at its turn a chunk is written to shared memory twice, as the
+    // raw tile (= tf32 hi operand) and as the lo tile.  (A cp.async ring would cost a third pass over
+    // shared memory - write raw, read raw, write lo - and shared-memory bandwidth is what bounds this
+    // kernel: the 12 MMAs of a chunk alone read 96 KB of operands from it.)
+    float4 bufA[2][kPieces], bufB[2][kPieces];
+    auto gload = [&](int c, float4 (&ba)[kPieces], float4 (&bb)[kPieces]) {
         if (c < C) {
-            unsigned char* ra = smem + LlSmem::kRaw + (c & 3) * 2 * LlSmem::kTile;
-            unsigned char* rb = ra + LlSmem::kTile;
 #pragma unroll
             for (int it = 0; it < kPieces; it++) {
                 const int idx = it * kLlThreads + t, row = idx >> 3, c4 = idx & 7;
-                cp_async16(ra + piece_off(it), Arows + (long)row * n + c * 32 + c4 * 4);
-                if (!same) cp_async16(rb + piece_off(it), Brows + (long)row * n + c * 32 + c4 * 4);
+                ba[it] = __ldg(reinterpret_cast<const float4*>(Arows + (long)row * n + c * 32 + c4 * 4));
+                if (!same) bb[it] = __ldg(reinterpret_cast<const float4*>(Brows + (long)row * n + c * 32 + c4 * 4));
             }
         }
-        cp_async_commit();  // always: keeps the group count uniform
     };
-    issue_loads(0);
-    issue_loads(1);
-    for (int c = 0; c < C; c++) {
-        if (c >= 2) {  // MMAs of chunk c-2 are done: raw stage (c+2)&3 and lo buffer c&1 are free
+    auto step = [&](int c, float4 (&ba)[kPieces], float4 (&bb)[kPieces]) {
+        if (c >= 2) {  // MMAs of chunk c-2 are done: raw and lo buffers of this parity are free
             mbar_wait(&bars[c & 1], (uint32_t)(((c - 2) >> 1) & 1));
             tc_fence_after();
         }
-        issue_loads(c + 2);
-        cp_async_wait<2>();  // this thread's pieces of chunk c have landed
-        unsigned char* ra = smem + LlSmem::kRaw + (c & 3) * 2 * LlSmem::kTile;
+        unsigned char* ra = smem + LlSmem::kRaw + (c & 1) * 2 * LlSmem::kTile;
         unsigned char* rb = same ? ra : ra + LlSmem::kTile;
         unsigned char* la = smem + LlSmem::kLo + (c & 1) * 2 * LlSmem::kTile;
         unsigned char* lb = same ? la : la + LlSmem::kTile;
 #pragma unroll
         for (int it = 0; it < kPieces; it++) {
             const int off = piece_off(it);
-            *reinterpret_cast<float4*>(la + off) = lo_of(*reinterpret_cast<const float4*>(ra + off));
-            if (!same) *reinterpret_cast<float4*>(lb + off) = lo_of(*reinterpret_cast<const float4*>(rb + off));
+            *reinterpret_cast<float4*>(ra + off) = ba[it];
+            *reinterpret_cast<float4*>(la + off) = lo_of(ba[it]);
+            if (!same) {
+                *reinterpret_cast<float4*>(rb + off) = bb[it];
+                *reinterpret_cast<float4*>(lb + off) = lo_of(bb[it]);
+            }
         }
+        gload(c + 2, ba, bb);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -544,6 +548,12 @@ blk_ll_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) 
             }
             umma_commit(&bars[c & 1]);
         }
+    };
+    gload(0, bufA[0], bufB[0]);
+    gload(1, bufA[1], bufB[1]);
+    for (int c = 0; c < C; c += 2) {  // C = 4 q is even
+        step(c, bufA[0], bufB[0]);
+        step(c + 1, bufA[1], bufB[1]);
     }
     // the C tile (from A) is fetched while the last chunks are still being multiplied
     const long coff = (long)r * NB * n + (long)q * NB;
@@ -556,7 +566,6 @@ blk_ll_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) 
     mbar_wait(&bars[(C - 2) & 1], (uint32_t)(((C - 2) >> 1) & 1));
     mbar_wait(&bars[(C - 1) & 1], (uint32_t)(((C - 1) >> 1) & 1));
     tc_fence_after();
-    cp_async_wait<0>();
     {
         float* stage = reinterpret_cast<float*>(smem);
         const int drow = (warp & 3) * 32 + lane;  // accumulator row = TMEM lane (warp % 4 selects the lane quarter)
