@@ -76,13 +76,17 @@ static int chol_dev(const float* A, float* L, int n, int64_t batch, int design, 
     if (!chol_variant(design, &variant)) return fail(HLSD_ERR_INVALID, "unknown Cholesky design");
     if (int rc = check_path(flags, &path)) return rc;
     // large right-looking problems go to the blocked tensor-core path unless a path was forced
-    if (path == HLSD_PATH_AUTO && variant == 0 && n >= 256 && n % 128 == 0 && batch <= 65535 &&
-        (((uintptr_t)A | (uintptr_t)L) & 15) == 0)
+    if (path == HLSD_PATH_AUTO && variant == 0 && n >= 256 && n % 128 == 0 && (((uintptr_t)A | (uintptr_t)L) & 15) == 0)
         path = HLSD_PATH_TENSOR;
     if (path == HLSD_PATH_BLOCKED || path == HLSD_PATH_TENSOR) {
         if (variant != 0) return fail(HLSD_ERR_UNSUPPORTED, "blocked Cholesky implements the right-looking designs only");
-        cudaError_t e = cholesky_blocked(A, L, n, (long)batch, path == HLSD_PATH_TENSOR, st);
-        if (e == cudaErrorNotSupported) return fail(HLSD_ERR_UNSUPPORTED, "the blocked tensor-core Cholesky needs n % 128 == 0, n >= 256, batch <= 65535 (HLSD_PATH_BLOCKED, the SIMT trailing update, is not built yet)");
+        cudaError_t e = cudaSuccess;
+        const int64_t kSlice = 32768;  // the blocked kernels index the batch with gridDim.y
+        for (int64_t b0 = 0; b0 < batch && e == cudaSuccess; b0 += kSlice) {
+            const int64_t cnt = batch - b0 < kSlice ? batch - b0 : kSlice;
+            e = cholesky_blocked(A + b0 * n * n, L + b0 * n * n, n, (long)cnt, path == HLSD_PATH_TENSOR, st);
+        }
+        if (e == cudaErrorNotSupported) return fail(HLSD_ERR_UNSUPPORTED, "the blocked tensor-core Cholesky needs n % 128 == 0, n >= 256 and 16-byte aligned buffers (HLSD_PATH_BLOCKED, the SIMT trailing update, is not built)");
         if (e != cudaSuccess) return cuda_fail(e, "cholesky_blocked");
         return 0;
     }
@@ -99,14 +103,19 @@ static int lu_dev(const float* A, float* L, float* U, int32_t* P, int n, int64_t
     if (n < 1 || batch < 0) return fail(HLSD_ERR_INVALID, "n must be >= 1 and batch >= 0");
     if (!lu_pivoting(design, &pivoting)) return fail(HLSD_ERR_INVALID, "unknown LU design");
     if (int rc = check_path(flags, &path)) return rc;
-    if (path == HLSD_PATH_AUTO && pivoting && n >= 256 && n <= 1024 && n % 128 == 0 && batch <= 65535 &&
+    if (path == HLSD_PATH_AUTO && pivoting && n >= 256 && n <= 1024 && n % 128 == 0 &&
         (((uintptr_t)A | (uintptr_t)L | (uintptr_t)U) & 15) == 0)
         path = HLSD_PATH_TENSOR;
     if (path == HLSD_PATH_BLOCKED) return fail(HLSD_ERR_UNSUPPORTED, "HLSD_PATH_BLOCKED (SIMT trailing update) is not built; use HLSD_PATH_TENSOR or HLSD_PATH_GLOBAL");
     if (path == HLSD_PATH_TENSOR) {
         if (!pivoting) return fail(HLSD_ERR_UNSUPPORTED, "the blocked LU implements the pivoted designs only");
-        cudaError_t e = lu_blocked(A, L, U, P, n, (long)batch, st);
-        if (e == cudaErrorNotSupported) return fail(HLSD_ERR_UNSUPPORTED, "the blocked tensor-core LU needs n % 128 == 0, 256 <= n <= 1024, batch <= 65535");
+        cudaError_t e = cudaSuccess;
+        const int64_t kSlice = 32768;
+        for (int64_t b0 = 0; b0 < batch && e == cudaSuccess; b0 += kSlice) {
+            const int64_t cnt = batch - b0 < kSlice ? batch - b0 : kSlice;
+            e = lu_blocked(A + b0 * n * n, L + b0 * n * n, U + b0 * n * n, P + b0 * n, n, (long)cnt, st);
+        }
+        if (e == cudaErrorNotSupported) return fail(HLSD_ERR_UNSUPPORTED, "the blocked tensor-core LU needs n % 128 == 0, 256 <= n <= 1024 and 16-byte aligned buffers");
         if (e != cudaSuccess) return cuda_fail(e, "lu_blocked");
         return 0;
     }
