@@ -121,6 +121,95 @@ qr_tpm_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// N lanes per matrix (square N = 16, 32): lane j keeps COLUMN j of R and ROW j of Q in registers.
+// A rotation of rows (lo, i) then touches two registers of every lane's R column and two of its Q
+// row - no data moves between lanes except the generating pair: the lane that owns column c
+// broadcasts it by shuffle (the systolic arrays stream (c, s) from the diagonal PE to the PEs on
+// its right, qr_v2.1/template/T_qr.cpp PE1 -> PE2; here every lane derives the same (c, s)).
+// Rotations run in the reference's sequential order (column by column, bottom up), so every element
+// sees the same operations in the same order: bit-identical.  Row indices are compile-time (the
+// row loop is unrolled and predicated on i > c), the column loop is a run-time loop.
+// ------------------------------------------------------------------------------------------------
+template <int N, int VARIANT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+qr_cols_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restrict__ R, long batch) {
+    constexpr int MPW = 32 / N;  // matrices per warp
+    constexpr int kSlot = N * N + 4;
+    constexpr uint32_t kRowBytes = N * 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* slabs = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * MPW * 2 * kSlot * 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = lane % N, m = lane / N, gbase = lane - j;
+    float* sR = slabs + ((size_t)warp * MPW + m) * 2 * kSlot;
+    float* sQ = sR + kSlot;
+    uint64_t* bar = bars + warp;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const long num_slabs = (batch + MPW - 1) / MPW;
+    uint32_t parity = 0;
+    for (long sl = (long)blockIdx.x * WARPS + warp; sl < num_slabs; sl += (long)gridDim.x * WARPS) {
+        const long m0 = sl * MPW;
+        const int valid = (int)min((long)MPW, batch - m0);
+        bulk_wait_read<0>();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * N * kRowBytes);
+        __syncwarp();
+        if (m < valid) bulk_g2s(sR + j * N, A + (m0 + m) * (long)(N * N) + j * N, kRowBytes, bar);
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        float r[N], q[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            r[i] = sR[i * N + j];  // column j of A
+            q[i] = (i == j) ? 1.0f : 0.0f;  // row j of Q = e_j
+        }
+        for (int c = 0; c < N - 1; c++) {
+            static_for<1, N>([&](auto ic) {
+                constexpr int i = N - decltype(ic)::value;  // N-1 down to 1
+                constexpr int lo = (VARIANT == 0) ? i - 1 : (i == 1 ? 0 : i - 2);
+                if (i > c) {  // warp-uniform
+                    // the generating pair lives in the lane that owns column c: broadcast it and let every lane
+                    // derive the same angle (all lanes then run the fast paths of sqrt / division together,
+                    // instead of one lane computing on real data and the others on unrelated values)
+                    float hi_v = __shfl_sync(0xffffffffu, r[i], gbase + c);
+                    float lo_v = __shfl_sync(0xffffffffu, r[lo], gbase + c);
+                    const bool skip = givens_skip<VARIANT>(hi_v);
+                    float cs, sn;
+                    givens_make(lo_v, hi_v, skip, cs, sn);
+                    if (j == c) {
+                        r[lo] = lo_v;  // mag (or unchanged when skipped)
+                        r[i] = hi_v;   // 0   (or unchanged when skipped)
+                    } else if (j > c) {
+                        givens_apply(cs, sn, r[lo], r[i]);
+                    }
+                    givens_apply(cs, sn, q[lo], q[i]);
+                }
+            });
+        }
+        __syncwarp();  // every lane has read its column from the slab
+        if (m < valid) {
+#pragma unroll
+            for (int i = 0; i < N; i++) sR[i * N + j] = r[i];
+            float4* q4 = reinterpret_cast<float4*>(sQ + j * N);
+#pragma unroll
+            for (int v = 0; v < N / 4; v++) q4[v] = make_float4(q[4 * v], q[4 * v + 1], q[4 * v + 2], q[4 * v + 3]);
+            fence_async_smem();
+        }
+        __syncwarp();
+        if (m < valid) {
+            bulk_s2g(R + (m0 + m) * (long)(N * N) + j * N, sR + j * N, kRowBytes);
+            bulk_s2g(Q + (m0 + m) * (long)(N * N) + j * N, sQ + j * N, kRowBytes);
+            bulk_commit();
+        }
+    }
+    bulk_wait_read<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
 // shared body: factor one matrix held in r (rows x ldr) / q (rows x ldq) with G threads.
 // cs: scratch for 2 * (rows/2 + 1) floats (the (c, s) pairs of one wavefront).
 // ------------------------------------------------------------------------------------------------
@@ -277,6 +366,22 @@ static cudaError_t launch_qr_tpm(const float* A, float* Q, float* R, long batch,
     return cudaGetLastError();
 }
 
+template <int N, int VARIANT>
+static cudaError_t launch_qr_cols(const float* A, float* Q, float* R, long batch, cudaStream_t st) {
+    constexpr int MPW = 32 / N;
+    constexpr int WARPS = (N == 16) ? 16 : 12;
+    const size_t smem = (size_t)WARPS * MPW * 2 * (N * N + 4) * 4 + WARPS * sizeof(uint64_t);
+    auto kern = qr_cols_kernel<N, VARIANT, WARPS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long num_slabs = (batch + MPW - 1) / MPW;
+    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (size_t)(227 * 1024) / (smem + 1024)));
+    long grid = std::min<long>((num_slabs + WARPS - 1) / WARPS, (long)sm_count() * ctas_per_sm);
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(A, Q, R, batch);
+    count_launch();
+    return cudaGetLastError();
+}
+
 static size_t qr_smem_per_matrix(int rows, int cols) {
     return ((size_t)rows * (cols | 1) + (size_t)rows * (rows | 1) + 2 * (rows / 2 + 2)) * 4;
 }
@@ -303,6 +408,9 @@ static cudaError_t qr_dispatch(const float* A, float* Q, float* R, int rows, int
     if (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM) {
         if (aligned && rows == 4 && cols == 4) return launch_qr_tpm<4, VARIANT>(A, Q, R, batch, st);
         if (aligned && rows == 8 && cols == 8) return launch_qr_tpm<8, VARIANT>(A, Q, R, batch, st);
+        if (aligned && rows == 16 && cols == 16) return launch_qr_cols<16, VARIANT>(A, Q, R, batch, st);
+        // (qr_cols_kernel<32> is correct but slower than the wavefront kernel: 16.5 M vs 20.1 M fact/s)
+        if (aligned && rows == 32 && cols == 32 && path == HLSD_PATH_TPM) return launch_qr_cols<32, VARIANT>(A, Q, R, batch, st);
         if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
     }
     const size_t per = qr_smem_per_matrix(rows, cols);

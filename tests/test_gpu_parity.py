@@ -19,7 +19,7 @@ QR_DESIGNS = ("qr_v1.1", "qr_v1.2", "qr_v2.1")
 
 def _paths_for(n, kind):
     paths = ["auto", "group", "global"]
-    if (kind == "chol" and n in (4, 8, 16, 32, 64)) or (kind == "lu" and n in (4, 8, 16, 32, 64)) or (kind == "qr" and n in (4, 8)):
+    if (kind == "chol" and n in (4, 8, 16, 32, 64)) or (kind == "lu" and n in (4, 8, 16, 32, 64)) or (kind == "qr" and n in (4, 8, 16, 32)):
         paths.append("tpm")
     return paths
 
