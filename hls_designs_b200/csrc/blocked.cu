@@ -145,11 +145,17 @@ blk_zero_upper_kernel(float* __restrict__ L, int n) {
 // L11 is collected in a shared-memory tile and written out row-wise at the end.
 // Plain fp32 FMA arithmetic (tensor path: tolerance-checked).
 // ------------------------------------------------------------------------------------------------
-// INV_ONLY: the block at S is an already finished UNIT lower triangular factor (blocked LU): only W = inv(L11)
-// is produced (no roots, no scaling, the unfinished-column updates are switched off, L is not written).
-template <bool INV_ONLY>
+// MODE 0: L11 and W as described.  MODE 1 (DIAG_INV_ONLY): the block at S is an already finished UNIT lower
+// triangular factor (blocked LU): only W = inv(L11) is produced (no roots, no scaling, the unfinished-column
+// updates are switched off, L is not written).  MODE 2 (DIAG_EXACT): Cholesky only, in the reference's exact
+// arithmetic (IEEE sqrt and division, separately rounded multiply and subtract, per-element update order
+// k ascending as in cholesky_v1.3/model4x4/chol.cpp:25-63): the bit-identical 128 x 128 kernel.
+enum { DIAG_CHOL_INV = 0, DIAG_INV_ONLY = 1, DIAG_EXACT = 2 };
+template <int MODE>
 __global__ void __launch_bounds__(512, 2)
 blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __restrict__ W, int n, int o) {
+    constexpr bool INV_ONLY = MODE == DIAG_INV_ONLY;
+    constexpr bool EXACT = MODE == DIAG_EXACT;
     extern __shared__ __align__(16) float dg_tile[];  // [NB][NB + 1]
     __shared__ float ubuf[2][NB];                     // ubuf[k & 1][i] = l_ik for i > k
     __shared__ float sdiag[2];                        // sdiag[k & 1] = l_kk
@@ -177,20 +183,22 @@ blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __res
             const int lk = k & 31;
             float* ub = ubuf[k & 1];
             if (w == kr) {  // this warp owns column k (all rows): root, scale, publish, re-seed with e_k
-                const float d = INV_ONLY ? 1.0f : sqrtf(__shfl_sync(0xffffffffu, v[AK][BK], lk));
+                const float d = INV_ONLY ? 1.0f : (EXACT ? xsqrt(__shfl_sync(0xffffffffu, v[AK][BK], lk))
+                                                         : sqrtf(__shfl_sync(0xffffffffu, v[AK][BK], lk)));
                 const float rd = INV_ONLY ? 1.0f : 1.0f / d;
                 if (l == 0) sdiag[k & 1] = d;
 #pragma unroll
                 for (int a = 0; a < 4; a++) {
                     const int i = l + 32 * a;
-                    const float lv = v[a][BK] * rd;
+                    const float lv = EXACT ? xdiv(v[a][BK], d) : v[a][BK] * rd;
                     if (i > k) ub[i] = lv;
                     dg_tile[i * ld + k] = (i > k) ? lv : (i == k ? d : 0.0f);
                     v[a][BK] = (i == k) ? 1.0f : 0.0f;
                 }
             }
             __syncthreads();
-            const float rd = INV_ONLY ? 1.0f : 1.0f / sdiag[k & 1];
+            const float rd = (INV_ONLY || EXACT) ? 1.0f : 1.0f / sdiag[k & 1];
+            (void)rd;
             // multipliers per column slot: slots b < BK hold columns j < 16 BK <= k (finished: w_kj, shuffled from
             // the row-k lane of this warp), slots b > BK hold columns j > k (l_jk from the column stream);
             // only slot BK needs a run-time test (j = w + 16 BK <= k  <=>  w <= kr)
@@ -198,14 +206,22 @@ blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __res
             static_for<0, 8>([&](auto bc) {
                 constexpr int b = decltype(bc)::value;
                 if constexpr (b < BK) {
-                    u[b] = __shfl_sync(0xffffffffu, v[AK][b], lk) * rd;
-                    if (l == lk) v[AK][b] = u[b];  // row k of W is final
+                    if constexpr (EXACT) {
+                        u[b] = 0.0f;
+                    } else {
+                        u[b] = __shfl_sync(0xffffffffu, v[AK][b], lk) * rd;
+                        if (l == lk) v[AK][b] = u[b];  // row k of W is final
+                    }
                 } else if constexpr (b > BK) {
                     u[b] = INV_ONLY ? 0.0f : ub[w + 16 * b];
                 } else {
                     if (w <= kr) {
-                        u[b] = __shfl_sync(0xffffffffu, v[AK][b], lk) * rd;
-                        if (l == lk) v[AK][b] = u[b];
+                        if constexpr (EXACT) {
+                            u[b] = 0.0f;
+                        } else {
+                            u[b] = __shfl_sync(0xffffffffu, v[AK][b], lk) * rd;
+                            if (l == lk) v[AK][b] = u[b];
+                        }
                     } else {
                         u[b] = INV_ONLY ? 0.0f : ub[w + 16 * b];
                     }
@@ -216,14 +232,21 @@ blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __res
                 const int i = l + 32 * AK;
                 const float lr = (i > k) ? ub[i] : 0.0f;
 #pragma unroll
-                for (int b = 0; b <= 2 * AK + 1; b++) v[AK][b] = fmaf(-lr, u[b], v[AK][b]);
+                for (int b = EXACT ? BK : 0; b <= 2 * AK + 1; b++) {
+                    if constexpr (EXACT) {
+                        if (i > k) v[AK][b] = xmsub(v[AK][b], lr, u[b]);  // rows <= k are not touched (0 * inf would be NaN)
+                    } else {
+                        v[AK][b] = fmaf(-lr, u[b], v[AK][b]);
+                    }
+                }
             }
             static_for<AK + 1, 4>([&](auto ac) {
                 constexpr int a = decltype(ac)::value;
                 const float lr = ub[l + 32 * a];
                 // columns j = w + 16 b > i are never needed: i <= 32 a + 31, so b <= 2 a + 1 suffices
 #pragma unroll
-                for (int b = 0; b <= 2 * a + 1; b++) v[a][b] = fmaf(-lr, u[b], v[a][b]);
+                for (int b = EXACT ? BK : 0; b <= 2 * a + 1; b++)
+                    v[a][b] = EXACT ? xmsub(v[a][b], lr, u[b]) : fmaf(-lr, u[b], v[a][b]);
             });
         }
     });
@@ -234,6 +257,7 @@ blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __res
             const int i = e >> 7, j = e & (NB - 1);
             blk[(long)i * n + j] = (j <= i) ? dg_tile[i * ld + j] : 0.0f;
         }
+    if (EXACT) return;
     __syncthreads();
 #pragma unroll
     for (int a = 0; a < 4; a++)
@@ -602,7 +626,7 @@ blk_ll_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) 
 static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int n, long batch, cudaStream_t st) {
     cudaFuncSetAttribute(blk_mma_kernel<MMA_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
     cudaFuncSetAttribute(blk_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LlSmem::kTotal);
-    cudaFuncSetAttribute(blk_diag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
+    cudaFuncSetAttribute(blk_diag_kernel<DIAG_CHOL_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
     const int panels = n / NB;
     const unsigned nb = (unsigned)batch;
     blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, nb), 256, 0, st>>>(L, n);
@@ -615,7 +639,7 @@ static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int
             blk_ll_kernel<<<dim3(panels - q, nb), kLlThreads, LlSmem::kTotal, st>>>(A, L, n, q);
             count_launch();
         }
-        blk_diag_kernel<false><<<nb, 512, kDiagSmem, st>>>(src, L, W, n, o);
+        blk_diag_kernel<DIAG_CHOL_INV><<<nb, 512, kDiagSmem, st>>>(src, L, W, n, o);
         count_launch();
         if (mt > 0) {
             blk_mma_kernel<MMA_TRSM><<<dim3(mt, nb), 256, MmaSmem::kTotal, st>>>(src, L, W, n, o);
@@ -626,6 +650,18 @@ static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// Bit-identical Cholesky of 128 x 128 matrices (right-looking designs): the register-tiled diagonal-block
+// kernel in exact arithmetic, one CTA per matrix.
+cudaError_t cholesky128_exact(const float* A, float* L, long batch, cudaStream_t st) {
+    cudaFuncSetAttribute(blk_diag_kernel<DIAG_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
+    for (long b0 = 0; b0 < batch; b0 += 1 << 20) {
+        const long cnt = std::min<long>(batch - b0, 1 << 20);
+        blk_diag_kernel<DIAG_EXACT><<<(unsigned)cnt, 512, kDiagSmem, st>>>(A + b0 * NB * NB, L + b0 * NB * NB, nullptr, NB, 0);
+        count_launch();
+    }
+    return cudaGetLastError();
+}
+
 // The workspaces come from the stream-ordered allocator; keep what it has reserved between calls
 // (the default pool hands memory back to the driver at every synchronisation point).
 static void keep_pool_memory() {
@@ -651,7 +687,7 @@ cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int us
     if ((e = cudaMallocAsync(&W, sizeof(float) * (size_t)batch * NB * NB, st)) != cudaSuccess) return e;
     cudaFuncSetAttribute(blk_mma_kernel<MMA_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
     cudaFuncSetAttribute(blk_mma_kernel<MMA_SYRK>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
-    cudaFuncSetAttribute(blk_diag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
+    cudaFuncSetAttribute(blk_diag_kernel<DIAG_CHOL_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
     static int right_looking = -1;  // HLSD_CHOL_RIGHT_LOOKING=1 (environment): the per-panel SYRK variant
     if (right_looking < 0) {
         const char* ev = getenv("HLSD_CHOL_RIGHT_LOOKING");
@@ -669,7 +705,7 @@ cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int us
         const int o = p * NB;
         const int mt = panels - p - 1;  // 128-row blocks below the diagonal block
         const float* src = (p == 0) ? A : L;
-        blk_diag_kernel<false><<<(unsigned)batch, 512, kDiagSmem, st>>>(src, L, W, n, o);
+        blk_diag_kernel<DIAG_CHOL_INV><<<(unsigned)batch, 512, kDiagSmem, st>>>(src, L, W, n, o);
         count_launch();
         if (mt > 0) {
             blk_mma_kernel<MMA_TRSM><<<dim3(mt, (unsigned)batch), 256, MmaSmem::kTotal, st>>>(src, L, W, n, o);
@@ -1140,7 +1176,7 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
     if ((e = cudaMallocAsync(&T1, sizeof(float) * (size_t)batch * n * NB, st)) != cudaSuccess) return e;
     const size_t unswap_smem = (size_t)2 * NB * (NB + 1) * sizeof(float) + (size_t)n * sizeof(int);
     cudaFuncSetAttribute(lu_unswap_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)unswap_smem);
-    cudaFuncSetAttribute(blk_diag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
+    cudaFuncSetAttribute(blk_diag_kernel<DIAG_INV_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
     cudaFuncSetAttribute(gemm_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
     cudaFuncSetAttribute(gemm_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
     const unsigned nb = (unsigned)batch;
@@ -1162,7 +1198,7 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
         }
         lu_swap_kernel<<<dim3((ncols + 127) / 128, nb), 128, n * sizeof(int), st>>>(U, P, n, o);
         count_launch();
-        blk_diag_kernel<true><<<nb, 512, kDiagSmem, st>>>(L, L, Winv, n, o);  // W = inv(L11), L11 unit lower
+        blk_diag_kernel<DIAG_INV_ONLY><<<nb, 512, kDiagSmem, st>>>(L, L, Winv, n, o);  // W = inv(L11), L11 unit lower
         count_launch();
         lu_transpose_kernel<0><<<dim3(ncols / 32, 4, nb), dim3(32, 8), 0, st>>>(U, T0, n, o);
         count_launch();

@@ -475,6 +475,8 @@ static cudaError_t launch_group(const float* A, float* L, int n, long batch, cud
 template <int VARIANT>
 static cudaError_t chol_dispatch(const float* A, float* L, int n, long batch, int path, cudaStream_t st) {
     const bool aligned = (((uintptr_t)A | (uintptr_t)L) & 15) == 0;
+    // 128 x 128, right-looking designs: the register-tiled CTA-per-matrix kernel (blocked.cu, exact mode)
+    if (VARIANT == 0 && n == 128 && (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM)) return cholesky128_exact(A, L, batch, st);
     if (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM) {
         if (aligned && n == 4) return launch_tpm<4, VARIANT>(A, L, batch, st);
         if (aligned && n == 8) return launch_tpm<8, VARIANT>(A, L, batch, st);

@@ -23,6 +23,9 @@ cudaError_t qr_exact(const float* A, float* Q, float* R, int rows, int cols, lon
 // on the tcgen05 tensor cores (use_tensor == 1).  cudaErrorNotSupported when the size is not served.
 cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int use_tensor, cudaStream_t st);
 
+// Bit-identical Cholesky (right-looking designs) of 128 x 128 matrices, register-tiled, one CTA per matrix.
+cudaError_t cholesky128_exact(const float* A, float* L, long batch, cudaStream_t st);
+
 // Blocked LU with partial pivoting, tensor-core trailing update (n % 128 == 0, 256 <= n <= 1024).
 cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long batch, cudaStream_t st);
 

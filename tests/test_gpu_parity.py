@@ -32,7 +32,10 @@ def test_cholesky_golden(golden_chol, n):
         key = f"L_{d}_{n}"
         if key not in golden_chol:
             continue
-        for path in _paths_for(n, "chol"):
+        paths = _paths_for(n, "chol")
+        if n == 128 and d != "cholesky_v2.2":
+            paths.append("tpm")  # the register-tiled 128x128 kernel serves the right-looking designs only
+        for path in paths:
             L = hd.cholesky(A, design=d, path=path)
             assert bits_equal(L, golden_chol[key]), f"{d} n={n} path={path}: {first_mismatch(L, golden_chol[key])}"
 
