@@ -92,13 +92,20 @@ chol_tpm_kernel(const float* __restrict__ A, float* __restrict__ L, long batch) 
     for (long s = (long)blockIdx.x * WARPS + warp; s < num_slabs; s += (long)gridDim.x * WARPS) {
         const long m0 = s * 32;
         const int valid = (int)min(32L, batch - m0);
-        // the bulk store that last read this slot (issued by this very thread) must have drained
-        bulk_wait_read<0>();
-        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * Cfg::kMatBytes);
-        __syncwarp();
-        if (lane < valid) bulk_g2s(slot, A + (m0 + lane) * (long)(N * N), Cfg::kMatBytes, bar);
-        mbar_wait(bar, parity);
-        parity ^= 1;
+        constexpr bool kCoalesced = N <= 4;  // 64-byte matrices: cooperative coalesced copies beat one bulk copy per matrix
+        if constexpr (kCoalesced) {
+            __syncwarp();  // the previous slab has been written out of the slots
+            slab_g2s<N * N / 4>(reinterpret_cast<float4*>(slab), reinterpret_cast<const float4*>(A + m0 * (long)(N * N)), valid, lane);
+            __syncwarp();
+        } else {
+            // the bulk store that last read this slot (issued by this very thread) must have drained
+            bulk_wait_read<0>();
+            if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * Cfg::kMatBytes);
+            __syncwarp();
+            if (lane < valid) bulk_g2s(slot, A + (m0 + lane) * (long)(N * N), Cfg::kMatBytes, bar);
+            mbar_wait(bar, parity);
+            parity ^= 1;
+        }
         if (lane < valid) {
             float a[N * (N + 1) / 2];
             const float4* s4 = reinterpret_cast<const float4*>(slot);
@@ -123,9 +130,15 @@ chol_tpm_kernel(const float* __restrict__ A, float* __restrict__ L, long batch) 
                     for (int t = 0; t < 4; t++) e[t] = (4 * q + t <= i) ? a[i * (i + 1) / 2 + 4 * q + t] : 0.0f;
                     d4[i * (N / 4) + q] = make_float4(e[0], e[1], e[2], e[3]);
                 }
-            fence_async_smem();
-            bulk_s2g(L + (m0 + lane) * (long)(N * N), slot, Cfg::kMatBytes);
-            bulk_commit();
+            if constexpr (!kCoalesced) {
+                fence_async_smem();
+                bulk_s2g(L + (m0 + lane) * (long)(N * N), slot, Cfg::kMatBytes);
+                bulk_commit();
+            }
+        }
+        if constexpr (kCoalesced) {
+            __syncwarp();
+            slab_s2g<N * N / 4>(reinterpret_cast<float4*>(L + m0 * (long)(N * N)), reinterpret_cast<const float4*>(slab), valid, lane);
         }
     }
     bulk_wait_read<0>();

@@ -39,7 +39,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
 lu_tpm_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restrict__ U, int* __restrict__ P,
               long batch, int pivoting) {
     constexpr int kSlot = N * N + 4;
-    constexpr int kMatBytes = N * N * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // per warp: slab for A (reused for L) and a slab for U
     float* slabs = reinterpret_cast<float*>(smem_raw);
@@ -58,12 +57,22 @@ lu_tpm_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restr
     for (long s = (long)blockIdx.x * WARPS + warp; s < num_slabs; s += (long)gridDim.x * WARPS) {
         const long m0 = s * 32;
         const int valid = (int)min(32L, batch - m0);
-        bulk_wait_read<0>();
-        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * kMatBytes);
-        __syncwarp();
-        if (lane < valid) bulk_g2s(slotA, A + (m0 + lane) * (long)(N * N), kMatBytes, bar);
-        mbar_wait(bar, parity);
-        parity ^= 1;
+        constexpr bool kCoalesced = N <= 4;  // 64-byte matrices: cooperative coalesced copies beat one bulk copy per matrix
+        constexpr uint32_t kMatBytes = N * N * 4;
+        float4* slabA = reinterpret_cast<float4*>(slabs + (size_t)warp * 2 * 32 * kSlot);
+        float4* slabU = slabA + 32 * (kSlot / 4);
+        if constexpr (kCoalesced) {
+            __syncwarp();
+            slab_g2s<N * N / 4>(slabA, reinterpret_cast<const float4*>(A + m0 * (long)(N * N)), valid, lane);
+            __syncwarp();
+        } else {
+            bulk_wait_read<0>();
+            if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * kMatBytes);
+            __syncwarp();
+            if (lane < valid) bulk_g2s(slotA, A + (m0 + lane) * (long)(N * N), kMatBytes, bar);
+            mbar_wait(bar, parity);
+            parity ^= 1;
+        }
         if (lane < valid) {
             float a[N][N];
             const float4* s4 = reinterpret_cast<const float4*>(slotA);
@@ -126,13 +135,20 @@ lu_tpm_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restr
                     l4[i * (N / 4) + q] = make_float4(l[0], l[1], l[2], l[3]);
                     u4[i * (N / 4) + q] = make_float4(u[0], u[1], u[2], u[3]);
                 }
-            fence_async_smem();
-            bulk_s2g(L + (m0 + lane) * (long)(N * N), slotA, kMatBytes);
-            bulk_s2g(U + (m0 + lane) * (long)(N * N), slotU, kMatBytes);
-            bulk_commit();
             int4* p4 = reinterpret_cast<int4*>(P + (m0 + lane) * (long)N);
 #pragma unroll
             for (int q = 0; q < N / 4; q++) p4[q] = make_int4(piv[4 * q], piv[4 * q + 1], piv[4 * q + 2], piv[4 * q + 3]);
+            if constexpr (!kCoalesced) {
+                fence_async_smem();
+                bulk_s2g(L + (m0 + lane) * (long)(N * N), slotA, kMatBytes);
+                bulk_s2g(U + (m0 + lane) * (long)(N * N), slotU, kMatBytes);
+                bulk_commit();
+            }
+        }
+        if constexpr (kCoalesced) {
+            __syncwarp();
+            slab_s2g<N * N / 4>(reinterpret_cast<float4*>(L + m0 * (long)(N * N)), slabA, valid, lane);
+            slab_s2g<N * N / 4>(reinterpret_cast<float4*>(U + m0 * (long)(N * N)), slabU, valid, lane);
         }
     }
     bulk_wait_read<0>();

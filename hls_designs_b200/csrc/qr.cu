@@ -49,7 +49,6 @@ template <int N, int VARIANT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 qr_tpm_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restrict__ R, long batch) {
     constexpr int kSlot = N * N + 4;
-    constexpr int kMatBytes = N * N * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* slabs = reinterpret_cast<float*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * 2 * 32 * kSlot * 4);
@@ -67,12 +66,22 @@ qr_tpm_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restr
     for (long sl = (long)blockIdx.x * WARPS + warp; sl < num_slabs; sl += (long)gridDim.x * WARPS) {
         const long m0 = sl * 32;
         const int valid = (int)min(32L, batch - m0);
-        bulk_wait_read<0>();
-        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * kMatBytes);
-        __syncwarp();
-        if (lane < valid) bulk_g2s(slotR, A + (m0 + lane) * (long)(N * N), kMatBytes, bar);
-        mbar_wait(bar, parity);
-        parity ^= 1;
+        constexpr bool kCoalesced = N <= 4;  // 64-byte matrices: cooperative coalesced copies beat one bulk copy per matrix
+        constexpr uint32_t kMatBytes = N * N * 4;
+        float4* slabR = reinterpret_cast<float4*>(slabs + (size_t)warp * 2 * 32 * kSlot);
+        float4* slabQ = slabR + 32 * (kSlot / 4);
+        if constexpr (kCoalesced) {
+            __syncwarp();
+            slab_g2s<N * N / 4>(slabR, reinterpret_cast<const float4*>(A + m0 * (long)(N * N)), valid, lane);
+            __syncwarp();
+        } else {
+            bulk_wait_read<0>();
+            if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * kMatBytes);
+            __syncwarp();
+            if (lane < valid) bulk_g2s(slotR, A + (m0 + lane) * (long)(N * N), kMatBytes, bar);
+            mbar_wait(bar, parity);
+            parity ^= 1;
+        }
         if (lane < valid) {
             float r[N][N], q[N][N];
             const float4* s4 = reinterpret_cast<const float4*>(slotR);
@@ -111,10 +120,17 @@ qr_tpm_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restr
                     r4[i * (N / 4) + v] = make_float4(r[i][4 * v], r[i][4 * v + 1], r[i][4 * v + 2], r[i][4 * v + 3]);
                     q4[i * (N / 4) + v] = make_float4(q[i][4 * v], q[i][4 * v + 1], q[i][4 * v + 2], q[i][4 * v + 3]);
                 }
-            fence_async_smem();
-            bulk_s2g(R + (m0 + lane) * (long)(N * N), slotR, kMatBytes);
-            bulk_s2g(Q + (m0 + lane) * (long)(N * N), slotQ, kMatBytes);
-            bulk_commit();
+            if constexpr (!kCoalesced) {
+                fence_async_smem();
+                bulk_s2g(R + (m0 + lane) * (long)(N * N), slotR, kMatBytes);
+                bulk_s2g(Q + (m0 + lane) * (long)(N * N), slotQ, kMatBytes);
+                bulk_commit();
+            }
+        }
+        if constexpr (kCoalesced) {
+            __syncwarp();
+            slab_s2g<N * N / 4>(reinterpret_cast<float4*>(R + m0 * (long)(N * N)), slabR, valid, lane);
+            slab_s2g<N * N / 4>(reinterpret_cast<float4*>(Q + m0 * (long)(N * N)), slabQ, valid, lane);
         }
     }
     bulk_wait_read<0>();
