@@ -207,3 +207,45 @@ def test_random_sweep_bit_exact():
         view.copy_(torch.from_numpy(A))
         L = hd.cholesky(view)
         assert bits_equal(L.cpu().numpy(), restate.cholesky(A))
+
+
+def test_full_size_lu_n64_batch_262144_properties():
+    """configs[2] at full size: every matrix is checked on the device through P-free properties (L unit
+    lower with |l| <= 1, U upper, the pivot sequence valid), 2048 matrices spread over the batch are
+    compared bit for bit with the oracle, and 64 of them are reconstructed (||A - P^T L U|| / ||A||)."""
+    import torch
+    batch, n = 262144, 64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randint(1, 101, (batch, n, n), generator=g, device="cuda").float()
+    L, U, P = hd.lu(A)
+    assert float(torch.triu(L, 1).abs().max()) == 0.0
+    assert bool((torch.diagonal(L, dim1=1, dim2=2) == 1.0).all())
+    assert float(L.abs().max()) <= 1.0
+    assert float(torch.tril(U, -1).abs().max()) == 0.0
+    ar = torch.arange(n, device="cuda", dtype=torch.int32)
+    assert bool((P >= ar).all()) and bool((P < n).all()) and bool((P[:, -1] == n - 1).all())
+    idx = torch.arange(0, batch, batch // 2048, device="cuda")
+    want = restate.lu(A[idx].cpu().numpy(), threads=8)
+    for got, w in zip((L[idx], U[idx], P[idx]), want):
+        assert bits_equal(got.cpu().numpy(), w)
+    Ah, Lh, Uh, Ph = (x[idx[:64]].cpu().numpy() for x in (A, L, U, P))
+    assert max(lu_residual(Ah[b], Lh[b], Uh[b], Ph[b]) for b in range(64)) < 5e-5
+
+
+def test_full_size_qr_128_batch_16384_properties():
+    """configs[3] at full size: ||A - QR|| / ||A|| and ||Q^T Q - I|| on the device for every matrix, R upper
+    triangular exactly, 64 matrices bit for bit against the oracle."""
+    import torch
+    batch, n = 16384, 128
+    g = torch.Generator(device="cuda").manual_seed(4)
+    A = torch.randint(1, 101, (batch, n, n), generator=g, device="cuda").float()
+    Q, R = hd.qr(A)
+    assert float(torch.tril(R, -1).abs().max()) == 0.0
+    res = (A.double() - Q.double() @ R.double()).flatten(1).norm(dim=1) / A.double().flatten(1).norm(dim=1)
+    assert float(res.max()) < 1e-5
+    eye = torch.eye(n, device="cuda", dtype=torch.float64)
+    orth = (Q.double().transpose(1, 2) @ Q.double() - eye).flatten(1).norm(dim=1)
+    assert float(orth.max()) < 1e-4
+    idx = torch.arange(0, batch, batch // 64, device="cuda")
+    wq, wr = restate.qr(A[idx].cpu().numpy(), threads=8)
+    assert bits_equal(Q[idx].cpu().numpy(), wq) and bits_equal(R[idx].cpu().numpy(), wr)

@@ -79,3 +79,27 @@ def test_tensor_lu_vs_oracle(n, batch):
             if same:
                 assert err < 1e-3
         assert P[:, 0].tolist() == want[2][:, 0].tolist()  # first column: no arithmetic yet, pivots must agree
+
+
+def test_full_size_tensor_paths_n1024_properties():
+    """configs[4] (N = 1024) on a 256-matrix slice of the batch: residuals on the device for every matrix,
+    structure of the factors, first matrices against the oracle within the documented tolerances."""
+    import torch
+    n, batch = 1024, 256
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.rand((batch, n, n), generator=g, device="cuda")
+    S = (0.5 * (A + A.transpose(1, 2)))
+    S.diagonal(dim1=1, dim2=2).add_(float(n))
+    L = hd.cholesky(S)
+    res = (S - L @ L.transpose(1, 2)).flatten(1).norm(dim=1) / S.flatten(1).norm(dim=1)
+    assert float(res.max()) < RESIDUAL_TOL and float(torch.triu(L, 1).abs().max()) == 0.0
+    want = restate.cholesky(S[:2].cpu().numpy(), threads=8)
+    assert np.abs(L[:2].cpu().numpy() - want).max() / np.abs(want).max() < ELEMENT_TOL
+    del L, S
+    B = torch.randint(1, 101, (batch, n, n), generator=g, device="cuda").float()
+    Ll, Uu, P = hd.lu(B)
+    assert float(torch.triu(Ll, 1).abs().max()) == 0.0 and float(Ll.abs().max()) <= 1.0 + 1e-6
+    assert float(torch.tril(Uu, -1).abs().max()) == 0.0
+    from conftest import lu_residual
+    Bh, Lh, Uh, Ph = (x[:3].cpu().numpy() for x in (B, Ll, Uu, P))
+    assert max(lu_residual(Bh[b], Lh[b], Uh[b], Ph[b]) for b in range(3)) < 5e-5
