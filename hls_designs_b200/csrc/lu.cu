@@ -341,16 +341,16 @@ lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
     constexpr int kSlot = N * N + 4;
     constexpr int kStrip = 9;    // 8 block columns + 1: lanes fall on distinct banks
     constexpr int kStripAll = (N * kStrip + 3) / 4 * 4;
-    constexpr int kPerMat = 2 * kSlot + kStripAll + N + 8;  // floats: A/L slab, U slab, strips, P, partials
+    constexpr int kPerMat = kSlot + 2 * N + kStripAll + N + 8;  // floats: A/L slab, 2 pivot-row buffers, strips, P, partials
     constexpr uint32_t kRowBytes = N * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* base = reinterpret_cast<float*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)MATS * kPerMat * 4);
     const int mat = threadIdx.x / N, r = threadIdx.x % N, lane = threadIdx.x & 31;
     float* sA = base + (size_t)mat * kPerMat;
-    float* sU = sA + kSlot;
-    float* sp = sU + kSlot + r * kStrip;
-    int* sP = reinterpret_cast<int*>(sU + kSlot + kStripAll);
+    float* sRow = sA + kSlot;  // [2][N]: the pivot row of step k in buffer k & 1
+    float* sp = sRow + 2 * N + r * kStrip;
+    int* sP = reinterpret_cast<int*>(sRow + 2 * N + kStripAll);
     PivotCand* part = reinterpret_cast<PivotCand*>(sP + N);  // [2 parities][WPM]
     uint64_t* bar = bars + mat;
     auto gsync = [&]() {
@@ -380,17 +380,15 @@ lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
                 a[4 * q] = v.x, a[4 * q + 1] = v.y, a[4 * q + 2] = v.z, a[4 * q + 3] = v.w;
             }
         }
-        gsync();  // operand in registers: the slab becomes L (identity), the other one U (zero)
+        gsync();  // operand in registers: the slab becomes L (identity)
         {
             float4* l4 = reinterpret_cast<float4*>(sA + r * N);
-            float4* u4 = reinterpret_cast<float4*>(sU + r * N);
 #pragma unroll
-            for (int q = 0; q < N / 4; q++) {
+            for (int q = 0; q < N / 4; q++)
                 l4[q] = make_float4(r == 4 * q ? 1.0f : 0.0f, r == 4 * q + 1 ? 1.0f : 0.0f, r == 4 * q + 2 ? 1.0f : 0.0f,
                                     r == 4 * q + 3 ? 1.0f : 0.0f);
-                u4[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            }
         }
+        float* ug = U + b * (long)(N * N);  // U rows go straight to global memory, one finished row per step
         int pos = r;
         gsync();
         static_for<0, N / 8>([&](auto kbc) {
@@ -420,12 +418,25 @@ lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
                 if (r == 0) sP[k] = p;
                 if (pos == p) pos = k;
                 else if (pos == k) pos = p;
-                float* urow = sU + k * N;
-                if (pos == k) {  // this lane holds the pivot row: publish columns >= k as row k of U
-                    for (int q = kr; q < 8; q++) urow[c0 + q] = sp[q];
+                float* urow = sRow + (k & 1) * N;
+                if (pos == k) {  // this lane holds the pivot row: publish columns >= k and store row k of U
+                    float4* ug4 = reinterpret_cast<float4*>(ug + k * N);
 #pragma unroll
-                    for (int j = c0 + 8; j < N; j += 4)
-                        *reinterpret_cast<float4*>(urow + j) = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+                    for (int j = 0; j < c0; j += 4) __stcs(ug4 + j / 4, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+                    float blkv[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        blkv[q] = (q >= kr) ? sp[q] : 0.0f;
+                        urow[c0 + q] = blkv[q];
+                    }
+                    __stcs(ug4 + c0 / 4, make_float4(blkv[0], blkv[1], blkv[2], blkv[3]));
+                    __stcs(ug4 + c0 / 4 + 1, make_float4(blkv[4], blkv[5], blkv[6], blkv[7]));
+#pragma unroll
+                    for (int j = c0 + 8; j < N; j += 4) {
+                        const float4 v4 = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+                        *reinterpret_cast<float4*>(urow + j) = v4;
+                        __stcs(ug4 + j / 4, v4);
+                    }
                 }
                 gsync();
                 if (pos > k) {
@@ -447,7 +458,6 @@ lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
         fence_async_smem();
         gsync();
         bulk_s2g(L + b * (long)(N * N) + r * N, sA + r * N, kRowBytes);
-        bulk_s2g(U + b * (long)(N * N) + r * N, sU + r * N, kRowBytes);
         if (r == 0) bulk_s2g(P + b * (long)N, sP, N * 4);
         bulk_commit();
     }
@@ -596,9 +606,11 @@ static cudaError_t launch_lu_rows(const float* A, float* L, float* U, int* P, lo
 
 template <int N>
 static cudaError_t launch_lu_lane(const float* A, float* L, float* U, int* P, long batch, int pivoting, cudaStream_t st) {
-    constexpr size_t per_mat = (size_t)(2 * (N * N + 4) + (N * 9 + 3) / 4 * 4 + N + 8) * 4;
+    constexpr size_t per_mat = (size_t)((N * N + 4) + 2 * N + (N * 9 + 3) / 4 * 4 + N + 8) * 4;
     constexpr int fit = (int)((227 * 1024 - 1024) / (per_mat + 8));
-    constexpr int MATS = fit * N > 1024 ? 1024 / N : fit;
+    // registers bound the residency before shared memory does: a row of N floats per lane plus ~40 more
+    constexpr int by_regs = 65536 / ((N + 40) * N);
+    constexpr int MATS = fit * N > 1024 ? 1024 / N : (fit < by_regs ? fit : by_regs);
     const size_t smem = MATS * per_mat + MATS * sizeof(uint64_t);
     auto kern = lu_lane_kernel<N, MATS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
