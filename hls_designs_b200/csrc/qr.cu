@@ -253,21 +253,26 @@ __device__ __forceinline__ void qr_factor(float* r, long ldr, float* q, long ldq
             }
             sync();
             // apply: thread (ty, tx) takes rotations k = ty, ty + GY, ... and elements x = tx, tx + GX, ...
-            // (columns of R to the right of c, then rows of Q); rotations of one step touch disjoint rows
+            // (columns of R to the right of c, then rows of Q); rotations of one step touch disjoint rows.
+            // Everything that does not depend on the rotation is hoisted: an element x is either column x of
+            // R (stride ldr between rows) or row x - cols of Q (stride 1 between columns).
             const int width = cols + rows;
             constexpr int GX = G > 256 ? 256 : G, GY = G / GX;
             const int tx = t % GX, ty = t / GX;
-#pragma unroll 2
-            for (int k = ty; k < nrot; k += GY) {
-                const int c = c_lo + k, i = rows - 1 - step + 2 * c;
-                const float cc = cs[2 * k], ss = cs[2 * k + 1];
-                for (int x = tx; x < width; x += GX) {
-                    if (x < cols) {
-                        if (x > c) givens_apply(cc, ss, r[(long)(i - 1) * ldr + x], r[(long)i * ldr + x]);
-                    } else {
-                        const int row = x - cols;
-                        givens_apply(cc, ss, q[(long)row * ldq + (i - 1)], q[(long)row * ldq + i]);
-                    }
+            const int i0 = rows - 1 - step + 2 * c_lo;  // row index of rotation k: i0 + 2 k
+            for (int x = tx; x < width; x += GX) {
+                const bool is_r = x < cols;
+                float* base = is_r ? r + x : q + (long)(x - cols) * ldq;
+                const int stride = is_r ? (int)ldr : 1;
+                const int kmax = is_r ? min(nrot, x - c_lo) : nrot;  // column x of R only takes rotations with c < x
+#pragma unroll 4
+                for (int k = ty; k < kmax; k += GY) {
+                    const float cc = cs[2 * k], ss = cs[2 * k + 1];
+                    float* p = base + (i0 + 2 * k - 1) * stride;
+                    float lo = p[0], hi = p[stride];
+                    givens_apply(cc, ss, lo, hi);
+                    p[0] = lo;
+                    p[stride] = hi;
                 }
             }
             sync();
