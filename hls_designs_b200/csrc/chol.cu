@@ -301,13 +301,14 @@ chol_group_kernel(const float* __restrict__ A, float* __restrict__ L, int n, lon
                 if (t == 0) w[k * ld + k] = d;
                 for (int i = k + 1 + t; i < n; i += G) w[i * ld + k] = xdiv(w[i * ld + k], d);
                 group_sync<G>(g);
-                // a[j][i] -= l[j][k] * l[i][k], k < i <= j  (flattened over the (j, i) rectangle)
-                const int m = n - k - 1;
-                for (int e = t; e < m * m; e += G) {
-                    int jj = e / m, ii = e - jj * m;
-                    if (ii <= jj) {
-                        int j = k + 1 + jj, i = k + 1 + ii;
-                        w[j * ld + i] = xmsub(w[j * ld + i], w[j * ld + k], w[i * ld + k]);
+                // a[j][i] -= l[j][k] * l[i][k], k < i <= j: a warp-wide strip of row j per inner loop
+                {
+                    constexpr int GY = G / 32;
+                    const int tx = t & 31, ty = t >> 5;
+                    for (int j = k + 1 + ty; j < n; j += GY) {
+                        float* wrow = w + j * ld;
+                        const float ljk = wrow[k];
+                        for (int i = k + 1 + tx; i <= j; i += 32) wrow[i] = xmsub(wrow[i], ljk, w[i * ld + k]);
                     }
                 }
                 group_sync<G>(g);
@@ -315,12 +316,13 @@ chol_group_kernel(const float* __restrict__ A, float* __restrict__ L, int n, lon
                 float d = w[k * ld + k];
                 for (int i = k + 1 + t; i < n; i += G) mcol[i] = xdiv(w[i * ld + k], d);
                 group_sync<G>(g);
-                const int m = n - k - 1;
-                for (int e = t; e < m * m; e += G) {
-                    int jj = e / m, ii = e - jj * m;
-                    if (ii <= jj) {
-                        int j = k + 1 + jj, i = k + 1 + ii;
-                        w[j * ld + i] = xmsub(w[j * ld + i], w[j * ld + k], mcol[i]);
+                {
+                    constexpr int GY = G / 32;
+                    const int tx = t & 31, ty = t >> 5;
+                    for (int j = k + 1 + ty; j < n; j += GY) {
+                        float* wrow = w + j * ld;
+                        const float ajk = wrow[k];
+                        for (int i = k + 1 + tx; i <= j; i += 32) wrow[i] = xmsub(wrow[i], ajk, mcol[i]);
                     }
                 }
                 group_sync<G>(g);

@@ -502,11 +502,15 @@ __device__ __forceinline__ void lu_eliminate(float* w, long ld, int n, int t, in
         const float diag = w[k * ld + k];
         for (int i = k + 1 + t; i < n; i += G) w[i * ld + k] = xdiv(w[i * ld + k], diag);
         sync();
-        const int m = n - k - 1;
-        for (long e = t; e < (long)m * m; e += G) {
-            int ii = (int)(e / m), jj = (int)(e - (long)ii * m);
-            long i = k + 1 + ii, j = k + 1 + jj;
-            w[i * ld + j] = xmsub(w[i * ld + j], w[i * ld + k], w[k * ld + j]);
+        {  // trailing update: a warp-wide strip of a row per inner loop (no index division)
+            constexpr int GY = G / 32;
+            const int tx = t & 31, ty = t >> 5;
+            const float* urow = w + k * ld;
+            for (int i = k + 1 + ty; i < n; i += GY) {
+                float* wrow = w + i * ld;
+                const float l = wrow[k];
+                for (int j = k + 1 + tx; j < n; j += 32) wrow[j] = xmsub(wrow[j], l, urow[j]);
+            }
         }
         sync();
     }
