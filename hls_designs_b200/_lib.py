@@ -27,6 +27,7 @@ SIGNATURES = {
     "hlsd_launch_count": (_i64, []),
     "hlsd_last_error": (ctypes.c_char_p, []),
     "hlsd_version": (ctypes.c_char_p, []),
+    "hlsd_selftest_division": (_i, [_vp, _vp, _i64, _vp, _vp]),
 }
 
 _lib = None

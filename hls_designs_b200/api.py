@@ -121,3 +121,16 @@ def qr(A, design="qr_v2.1", path="auto"):
 
 def launch_count():
     return int(_lib.load().hlsd_launch_count())
+
+
+def selftest_division(num, den):
+    """(mismatches, fast_pairs) of the kernels' shared-divisor division against IEEE division over two
+    equally long float32 CUDA tensors (diagnostic; see include/hlsd.h)."""
+    import torch
+    assert num.is_cuda and den.is_cuda and num.dtype == den.dtype == torch.float32 and num.numel() == den.numel()
+    num, den = num.contiguous(), den.contiguous()
+    out = torch.zeros(2, dtype=torch.int64, device=num.device)
+    with torch.cuda.device(num.device):
+        _lib.check(_lib.load().hlsd_selftest_division(num.data_ptr(), den.data_ptr(), num.numel(), out.data_ptr(), _stream(num)))
+    bad, fast = out.tolist()
+    return bad, fast

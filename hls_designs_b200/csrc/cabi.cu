@@ -323,4 +323,11 @@ int64_t hlsd_launch_count(void) { return g_launches.load(std::memory_order_relax
 const char* hlsd_last_error(void) { return g_err.c_str(); }
 const char* hlsd_version(void) { return "hlsd 0.1 (sm_100a)"; }
 
+int hlsd_selftest_division(const float* num, const float* den, int64_t count, int64_t* out2, void* stream) {
+    if (!num || !den || !out2 || count < 0) return fail(HLSD_ERR_INVALID, "hlsd_selftest_division: bad argument");
+    cudaError_t e = hlsd::selftest_division(num, den, (long)count, reinterpret_cast<long long*>(out2), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "selftest_division");
+    return 0;
+}
+
 }  // extern "C"

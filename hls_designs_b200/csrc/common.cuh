@@ -29,6 +29,36 @@ __device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b)
 __device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float xsqrt(float a) { return __fsqrt_rn(a); }
+// IEEE division of several numerators by one divisor.  The reciprocal and its Newton step are computed once;
+// each quotient then costs three operations: q0 = a*r, rem = a - b*q0 (exact, fused), q = q0 + rem*r.  This is
+// the sequence nvcc itself emits for `div.rn.f32` on its fast path (MUFU.RCP + 5 FFMA), where it is guarded
+// by a range check (FCHK) that sends zeros, subnormals, infinities, NaNs and extreme exponents to a slow
+// subroutine; here the guard is `in_range` (a conservative sub-range of the fast path's), and anything
+// outside falls back to __fdiv_rn.  Both give the correctly rounded quotient, so results do not change.
+struct SharedDivisor {
+    float b, r;
+    bool ok;
+};
+__device__ __forceinline__ bool div_in_range(float x) {
+    const float ax = fabsf(x);
+    return ax >= 0x1p-60f && ax <= 0x1p60f;
+}
+__device__ __forceinline__ SharedDivisor make_divisor(float b) {
+    float r0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(b));
+    const float e = __fmaf_rn(-b, r0, 1.0f);
+    return SharedDivisor{b, __fmaf_rn(r0, e, r0), div_in_range(b)};
+}
+__device__ __forceinline__ float fast_quotient(float a, const SharedDivisor& d) {
+    const float q0 = __fmul_rn(a, d.r);
+    const float rem = __fmaf_rn(-d.b, q0, a);
+    return __fmaf_rn(d.r, rem, q0);
+}
+// one numerator (the checked form)
+__device__ __forceinline__ float xdiv(float a, const SharedDivisor& d) {
+    return (d.ok && div_in_range(a)) ? fast_quotient(a, d) : __fdiv_rn(a, d.b);
+}
+
 // a - b*c, two roundings
 __device__ __forceinline__ float xmsub(float a, float b, float c) { return __fsub_rn(a, __fmul_rn(b, c)); }
 

@@ -29,4 +29,8 @@ cudaError_t cholesky128_exact(const float* A, float* L, long batch, cudaStream_t
 // Blocked LU with partial pivoting, tensor-core trailing update (n % 128 == 0, 256 <= n <= 1024).
 cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long batch, cudaStream_t st);
 
+// Self-check: shared-divisor division (common.cuh) vs IEEE division over `count` device-resident pairs;
+// out2[0] = bitwise mismatches, out2[1] = pairs served by the fast path (device memory, 2 x int64).
+cudaError_t selftest_division(const float* num, const float* den, long count, long long* out2, cudaStream_t st);
+
 }  // namespace hlsd

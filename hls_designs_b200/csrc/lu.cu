@@ -204,7 +204,7 @@ lu_rows_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
         __syncwarp();
         if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * kMatBytes);
         __syncwarp();
-        if (m < valid) bulk_g2s(sA + r * (kPart / 4), A + (m0 + m) * (long)(N * N) + r * (kPart / 4), kPart, bar);
+        if (m < valid && r == 0) bulk_g2s(sA, A + (m0 + m) * (long)(N * N), kMatBytes, bar);  // one copy per matrix
         mbar_wait(bar, parity);
         parity ^= 1;
         float a[T][N];
@@ -320,6 +320,162 @@ lu_rows_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
             bulk_s2g(L + (m0 + m) * (long)(N * N) + r * (kPart / 4), sA + r * (kPart / 4), kPart);
             bulk_s2g(U + (m0 + m) * (long)(N * N) + r * (kPart / 4), sU + r * (kPart / 4), kPart);
             if (r == 0) bulk_s2g(P + (m0 + m) * (long)N, sP, N * 4);
+            bulk_commit();
+        }
+    }
+    bulk_wait_read<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// R lanes per matrix, everything in registers (N = 8, 16, 32): as lu_rows_kernel, but the step loop
+// is unrolled at compile time, so no column ever needs a run-time register index and the strips
+// disappear.  The pivot row travels by shuffle: its owner lane (found by a ballot over the group)
+// selects it from its T rows and broadcasts it column by column; the owner also stores it as row
+// k of U.  Rows that have already served as pivot rows are dead data and are updated along with
+// the live ones (no predication); only their L stores are masked.
+// ------------------------------------------------------------------------------------------------
+template <int N, int R, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restrict__ U, int* __restrict__ P,
+               long batch, int pivoting) {
+    constexpr int MPW = 32 / R;  // matrices per warp
+    constexpr int T = N / R;     // data rows per lane
+    constexpr int kSlot = N * N + 4;
+    constexpr int kPerMat = 2 * kSlot + N;  // floats: A/L slab, U slab, P
+    constexpr uint32_t kMatBytes = N * N * 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* base = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * MPW * kPerMat * 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = lane % R, m = lane / R, gbase = lane - r;
+    float* sA = base + ((size_t)warp * MPW + m) * kPerMat;  // operand, then L
+    float* sU = sA + kSlot;
+    int* sP = reinterpret_cast<int*>(sU + kSlot);
+    uint64_t* bar = bars + warp;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const long num_slabs = (batch + MPW - 1) / MPW;
+    uint32_t parity = 0;
+    for (long s = (long)blockIdx.x * WARPS + warp; s < num_slabs; s += (long)gridDim.x * WARPS) {
+        const long m0 = s * MPW;
+        const int valid = (int)min((long)MPW, batch - m0);
+        bulk_wait_read<0>();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * kMatBytes);
+        __syncwarp();
+        if (m < valid && r == 0) bulk_g2s(sA, A + (m0 + m) * (long)(N * N), kMatBytes, bar);  // one copy per matrix
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        float a[T][N];
+        int pos[T];
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            pos[t] = t * R + r;
+            const float4* row4 = reinterpret_cast<const float4*>(sA + (t * R + r) * N);
+#pragma unroll
+            for (int q = 0; q < N / 4; q++) {
+                float4 v = row4[q];
+                a[t][4 * q] = v.x, a[t][4 * q + 1] = v.y, a[t][4 * q + 2] = v.z, a[t][4 * q + 3] = v.w;
+            }
+        }
+        __syncwarp();  // the operand is in registers: the slab becomes L (diagonal and above), the other U (below)
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            const int i = t * R + r;
+            float4* l4 = reinterpret_cast<float4*>(sA + i * N);
+            float4* u4 = reinterpret_cast<float4*>(sU + i * N);
+#pragma unroll
+            for (int q = 0; q < N / 4; q++) {
+                if (q >= (t * R) / 4 && q >= i / 4)
+                    l4[q] = make_float4(i == 4 * q ? 1.0f : 0.0f, i == 4 * q + 1 ? 1.0f : 0.0f, i == 4 * q + 2 ? 1.0f : 0.0f,
+                                        i == 4 * q + 3 ? 1.0f : 0.0f);
+                if (q <= (t * R + R - 1) / 4 && q < i / 4) u4[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+        }
+        __syncwarp();
+        float u[N];
+        static_for<0, N>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            int p = k;
+            if constexpr (k < N - 1) {
+                if (pivoting) {
+                    PivotCand c{-2.0f, 0x7fffffff};
+#pragma unroll
+                    for (int t = 0; t < T; t++)
+                        if (pos[t] >= k) c = pivot_better(c, PivotCand{pivot_key(a[t][k], pos[t] == k), pos[t]});
+#pragma unroll
+                    for (int off = R / 2; off > 0; off >>= 1) {
+                        PivotCand o{__shfl_xor_sync(0xffffffffu, c.v, off), __shfl_xor_sync(0xffffffffu, c.i, off)};
+                        c = pivot_better(c, o);
+                    }
+                    p = c.i;
+                }
+            }
+            if (r == 0) sP[k] = p;
+            bool isp[T];
+            bool mine = false;
+#pragma unroll
+            for (int t = 0; t < T; t++) {
+                if (pos[t] == p) pos[t] = k;
+                else if (pos[t] == k) pos[t] = p;
+                isp[t] = pos[t] == k;
+                mine |= isp[t];
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, mine);
+            const int owner = gbase + __ffs((bal >> gbase) & ((1u << R) - 1u)) - 1;
+            // pivot row: selected from the owner's rows, broadcast over the group, stored as row k of U
+            float own[N];
+#pragma unroll
+            for (int j = k; j < N; j++) {
+                float v = a[0][j];
+#pragma unroll
+                for (int t = 1; t < T; t++) v = isp[t] ? a[t][j] : v;
+                own[j] = v;
+                u[j] = __shfl_sync(0xffffffffu, v, owner);
+            }
+            if (mine) {
+                float4* u4 = reinterpret_cast<float4*>(sU + k * N);
+#pragma unroll
+                for (int q = k / 4; q < N / 4; q++)
+                    u4[q] = make_float4(4 * q >= k ? own[4 * q >= k ? 4 * q : k] : 0.0f,
+                                        4 * q + 1 >= k ? own[4 * q + 1 >= k ? 4 * q + 1 : k] : 0.0f,
+                                        4 * q + 2 >= k ? own[4 * q + 2 >= k ? 4 * q + 2 : k] : 0.0f, own[4 * q + 3]);
+            }
+            if constexpr (k < N - 1) {
+                const float piv = u[k];
+                const SharedDivisor dv = make_divisor(piv);
+                // dead rows divide the pivot by itself: a zero numerator would take the slow division path
+                float num[T], lm[T];
+                bool ok = dv.ok;
+#pragma unroll
+                for (int t = 0; t < T; t++) {
+                    num[t] = pos[t] > k ? a[t][k] : piv;
+                    ok &= div_in_range(num[t]);
+                }
+                if (ok) {
+#pragma unroll
+                    for (int t = 0; t < T; t++) lm[t] = fast_quotient(num[t], dv);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < T; t++) lm[t] = xdiv(num[t], piv);
+                }
+#pragma unroll
+                for (int t = 0; t < T; t++) {
+                    if (pos[t] > k) sA[pos[t] * N + k] = lm[t];
+#pragma unroll
+                    for (int j = k + 1; j < N; j++) a[t][j] = xmsub(a[t][j], lm[t], u[j]);
+                }
+            }
+        });
+        fence_async_smem();
+        __syncwarp();
+        if (m < valid) {  // three stores per matrix, issued by three different lanes of its group
+            if (r == 0) bulk_s2g(L + (m0 + m) * (long)(N * N), sA, kMatBytes);
+            if (r == 1) bulk_s2g(U + (m0 + m) * (long)(N * N), sU, kMatBytes);
+            if (r == R - 1) bulk_s2g(P + (m0 + m) * (long)N, sP, N * 4);
             bulk_commit();
         }
     }
@@ -608,6 +764,22 @@ static cudaError_t launch_lu_rows(const float* A, float* L, float* U, int* P, lo
     return cudaGetLastError();
 }
 
+template <int N, int R, int WARPS>
+static cudaError_t launch_lu_regs(const float* A, float* L, float* U, int* P, long batch, int pivoting, cudaStream_t st) {
+    constexpr int MPW = 32 / R;
+    constexpr size_t per_warp = (size_t)MPW * (2 * (N * N + 4) + N) * 4;
+    static_assert(WARPS * per_warp + WARPS * 8 <= 227 * 1024, "slabs do not fit");
+    const size_t smem = WARPS * per_warp + WARPS * sizeof(uint64_t);
+    auto kern = lu_regs_kernel<N, R, WARPS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long num_slabs = (batch + MPW - 1) / MPW;
+    long grid = std::min<long>((num_slabs + WARPS - 1) / WARPS, (long)sm_count());
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(A, L, U, P, batch, pivoting);
+    count_launch();
+    return cudaGetLastError();
+}
+
 template <int N>
 static cudaError_t launch_lu_lane(const float* A, float* L, float* U, int* P, long batch, int pivoting, cudaStream_t st) {
     constexpr size_t per_mat = (size_t)((N * N + 4) + 2 * N + (N * 9 + 3) / 4 * 4 + N + 8) * 4;
@@ -657,7 +829,10 @@ cudaError_t lu_exact(const float* A, float* L, float* U, int* P, int n, long bat
     if (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM) {
         if (aligned && n == 4) return launch_lu_tpm<4>(A, L, U, P, batch, pivoting, st);
         if (aligned && n == 8) return launch_lu_tpm<8>(A, L, U, P, batch, pivoting, st);
-        if (aligned && n == 16) return launch_lu_rows<16, 4>(A, L, U, P, batch, pivoting, st);
+        if (aligned && n == 16)
+            return lu_mode() == 1 ? launch_lu_rows<16, 4>(A, L, U, P, batch, pivoting, st)
+                 : lu_mode() == 2 ? launch_lu_regs<16, 2, 6>(A, L, U, P, batch, pivoting, st)
+                                  : launch_lu_regs<16, 4, 12>(A, L, U, P, batch, pivoting, st);
         if (aligned && n == 32) return lu_mode() == 1 ? launch_lu_rows<32, 16>(A, L, U, P, batch, pivoting, st)
                                                        : launch_lu_lane<32>(A, L, U, P, batch, pivoting, st);
         if (aligned && n == 64) return lu_mode() == 1 ? launch_lu_rows<64, 32>(A, L, U, P, batch, pivoting, st)

@@ -98,6 +98,12 @@ int64_t hlsd_launch_count(void);           /* kernels launched by this library s
 const char* hlsd_last_error(void);         /* thread-local, never NULL */
 const char* hlsd_version(void);
 
+/* ---- self-checks (diagnostics; no counterpart in the reference) ----
+ * The exact kernels divide several numerators by one pivot with a shared reciprocal (csrc/common.cuh).
+ * This compares that division with IEEE division, bit for bit, over `count` pairs of DEVICE floats.
+ * out2 (device, 2 x int64): [0] = mismatches (must be 0), [1] = pairs served by the fast sequence. */
+int hlsd_selftest_division(const float* num, const float* den, int64_t count, int64_t* out2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
