@@ -5,7 +5,9 @@
 // tests), so one arithmetic serves the three designs.  `pivoting == 0` skips the search (P[k] = k).
 //
 // Kernels:
-//   lu_tpm_kernel<N>      thread-per-matrix in registers, N in {4, 8}: bulk-copy staged slabs.
+//   lu_tpm_kernel<N>      thread-per-matrix in registers, N = 4 (and 8 for A/B runs): staged slabs.
+//   lu_regs_kernel<N,R>   R lanes per matrix, all in registers, N in {8, 16, 32}: pivot row by shuffle.
+//   lu_lane_kernel<N>     one lane per row, N = 64 (two warps per matrix).
 //   lu_group_kernel<G>    G threads per matrix, matrix resident in shared memory.
 //   lu_global_kernel      one CTA per matrix, in place in global memory (any N; exact; slow).
 #include <cstdlib>
@@ -334,10 +336,10 @@ lu_rows_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
 // k of U.  Rows that have already served as pivot rows are dead data and are updated along with
 // the live ones (no predication); only their L stores are masked.
 // ------------------------------------------------------------------------------------------------
-template <int N, int R, int WARPS>
+template <int N, int R, int WARPS, bool PIVOT>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restrict__ U, int* __restrict__ P,
-               long batch, int pivoting) {
+               long batch) {
     constexpr int MPW = 32 / R;  // matrices per warp
     constexpr int T = N / R;     // data rows per lane
     constexpr int kSlot = N * N + 4;
@@ -397,23 +399,24 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
         }
         __syncwarp();
         float u[N];
+        // pivot search over column k (rows at positions >= k): butterfly arg-max over the group
+        auto search = [&](auto kc) -> int {
+            constexpr int k = decltype(kc)::value;
+            if constexpr (!PIVOT || k >= N - 1) return k;
+            PivotCand c{-2.0f, 0x7fffffff};
+#pragma unroll
+            for (int t = 0; t < T; t++)
+                if (pos[t] >= k) c = pivot_better(c, PivotCand{pivot_key(a[t][k], pos[t] == k), pos[t]});
+#pragma unroll
+            for (int off = R / 2; off > 0; off >>= 1) {
+                PivotCand o{__shfl_xor_sync(0xffffffffu, c.v, off), __shfl_xor_sync(0xffffffffu, c.i, off)};
+                c = pivot_better(c, o);
+            }
+            return c.i;
+        };
+        int p = search(std::integral_constant<int, 0>{});
         static_for<0, N>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
-            int p = k;
-            if constexpr (k < N - 1) {
-                if (pivoting) {
-                    PivotCand c{-2.0f, 0x7fffffff};
-#pragma unroll
-                    for (int t = 0; t < T; t++)
-                        if (pos[t] >= k) c = pivot_better(c, PivotCand{pivot_key(a[t][k], pos[t] == k), pos[t]});
-#pragma unroll
-                    for (int off = R / 2; off > 0; off >>= 1) {
-                        PivotCand o{__shfl_xor_sync(0xffffffffu, c.v, off), __shfl_xor_sync(0xffffffffu, c.i, off)};
-                        c = pivot_better(c, o);
-                    }
-                    p = c.i;
-                }
-            }
             if (r == 0) sP[k] = p;
             bool isp[T];
             bool mine = false;
@@ -425,7 +428,7 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
                 mine |= isp[t];
             }
             const unsigned bal = __ballot_sync(0xffffffffu, mine);
-            const int owner = gbase + __ffs((bal >> gbase) & ((1u << R) - 1u)) - 1;
+            const int owner = gbase + __ffs((bal >> gbase) & (R == 32 ? 0xffffffffu : (1u << (R & 31)) - 1u)) - 1;
             // pivot row: selected from the owner's rows, broadcast over the group, stored as row k of U
             float own[N];
 #pragma unroll
@@ -462,11 +465,16 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
 #pragma unroll
                     for (int t = 0; t < T; t++) lm[t] = xdiv(num[t], piv);
                 }
+                // column k+1 first: the next step's pivot search only needs that one and its shuffles
+                // overlap the rest of the update (one straight-line block, the scheduler interleaves)
+#pragma unroll
+                for (int t = 0; t < T; t++) a[t][k + 1] = xmsub(a[t][k + 1], lm[t], u[k + 1]);
+                p = search(std::integral_constant<int, k + 1>{});
 #pragma unroll
                 for (int t = 0; t < T; t++) {
                     if (pos[t] > k) sA[pos[t] * N + k] = lm[t];
 #pragma unroll
-                    for (int j = k + 1; j < N; j++) a[t][j] = xmsub(a[t][j], lm[t], u[j]);
+                    for (int j = k + 2; j < N; j++) a[t][j] = xmsub(a[t][j], lm[t], u[j]);
                 }
             }
         });
@@ -770,12 +778,12 @@ static cudaError_t launch_lu_regs(const float* A, float* L, float* U, int* P, lo
     constexpr size_t per_warp = (size_t)MPW * (2 * (N * N + 4) + N) * 4;
     static_assert(WARPS * per_warp + WARPS * 8 <= 227 * 1024, "slabs do not fit");
     const size_t smem = WARPS * per_warp + WARPS * sizeof(uint64_t);
-    auto kern = lu_regs_kernel<N, R, WARPS>;
+    auto kern = pivoting ? lu_regs_kernel<N, R, WARPS, true> : lu_regs_kernel<N, R, WARPS, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long num_slabs = (batch + MPW - 1) / MPW;
     long grid = std::min<long>((num_slabs + WARPS - 1) / WARPS, (long)sm_count());
-    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(A, L, U, P, batch, pivoting);
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(A, L, U, P, batch);
     count_launch();
     return cudaGetLastError();
 }
@@ -812,7 +820,7 @@ static cudaError_t launch_lu_group(const float* A, float* L, float* U, int* P, i
     return cudaGetLastError();
 }
 
-// HLSD_LU_ROWS=1 (environment) selects the two-rows-per-lane kernel for N = 32/64 (A/B measurements)
+// HLSD_LU_ROWS (environment): older kernel variants for A/B measurements, see lu_exact
 static int lu_mode() {
     static int mode = -1;
     if (mode < 0) {
@@ -828,13 +836,17 @@ cudaError_t lu_exact(const float* A, float* L, float* U, int* P, int n, long bat
     const bool aligned = (((uintptr_t)A | (uintptr_t)L | (uintptr_t)U | (uintptr_t)P) & 15) == 0;
     if (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM) {
         if (aligned && n == 4) return launch_lu_tpm<4>(A, L, U, P, batch, pivoting, st);
-        if (aligned && n == 8) return launch_lu_tpm<8>(A, L, U, P, batch, pivoting, st);
+        // HLSD_LU_ROWS selects the older kernels for A/B measurements (1: strips in shared memory, 2: one lane per row)
+        if (aligned && n == 8)
+            return lu_mode() == 1 ? launch_lu_tpm<8>(A, L, U, P, batch, pivoting, st)
+                                  : launch_lu_regs<8, 2, 20>(A, L, U, P, batch, pivoting, st);
         if (aligned && n == 16)
             return lu_mode() == 1 ? launch_lu_rows<16, 4>(A, L, U, P, batch, pivoting, st)
-                 : lu_mode() == 2 ? launch_lu_regs<16, 2, 6>(A, L, U, P, batch, pivoting, st)
                                   : launch_lu_regs<16, 4, 12>(A, L, U, P, batch, pivoting, st);
-        if (aligned && n == 32) return lu_mode() == 1 ? launch_lu_rows<32, 16>(A, L, U, P, batch, pivoting, st)
-                                                       : launch_lu_lane<32>(A, L, U, P, batch, pivoting, st);
+        if (aligned && n == 32)
+            return lu_mode() == 1 ? launch_lu_rows<32, 16>(A, L, U, P, batch, pivoting, st)
+                 : lu_mode() == 2 ? launch_lu_lane<32>(A, L, U, P, batch, pivoting, st)
+                                  : launch_lu_regs<32, 16, 10>(A, L, U, P, batch, pivoting, st);
         if (aligned && n == 64) return lu_mode() == 1 ? launch_lu_rows<64, 32>(A, L, U, P, batch, pivoting, st)
                                                        : launch_lu_lane<64>(A, L, U, P, batch, pivoting, st);
         if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
