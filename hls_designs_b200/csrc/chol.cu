@@ -182,8 +182,8 @@ chol_rows_kernel(const float* __restrict__ A, float* __restrict__ L, long batch)
         __syncwarp();  // all lanes' previous stores have drained before anyone refills the slab
         if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * Cfg::kMatBytes);
         __syncwarp();
-        if (m < valid)
-            bulk_g2s(slot + r * (kPart / 4), A + (m0 + m) * (long)(N * N) + r * (kPart / 4), kPart, bar);
+        // each lane moves 1/R of its matrix: many small copies in flight measured faster than one per matrix
+        if (m < valid) bulk_g2s(slot + r * (kPart / 4), A + (m0 + m) * (long)(N * N) + r * (kPart / 4), kPart, bar);
         mbar_wait(bar, parity);
         parity ^= 1;
         // a[t][j]: row i = t*R + r, columns 0 .. t*R + R - 1 (static bound; j > i is scratch)
@@ -204,7 +204,9 @@ chol_rows_kernel(const float* __restrict__ A, float* __restrict__ L, long batch)
             constexpr int k = decltype(kc)::value;
             constexpr int tk = k / R, rk = k % R;
             // pivot: owner lane rk, local row tk
-            float piv = a[tk][k];
+            // lanes that do not own row k hold scratch there (possibly zero or negative): they root 1.0 instead,
+            // so that no lane leaves the fast path of the square root
+            float piv = (r == rk) ? a[tk][k] : 1.0f;
             if constexpr (VARIANT == 0) piv = xsqrt(piv);
             const float d = __shfl_sync(0xffffffffu, piv, gbase + rk);
             if constexpr (VARIANT == 0) {
@@ -214,12 +216,28 @@ chol_rows_kernel(const float* __restrict__ A, float* __restrict__ L, long batch)
             }
             // own entries of column k below the diagonal: rows i = t*R + r > k
             float own[T];
+            {
+                const SharedDivisor dv = make_divisor(d);
+                // local row tk is scratch in lanes r <= rk (rows <= k): divide the pivot by itself there
+                float num[T];
+                bool ok = dv.ok;
 #pragma unroll
-            for (int t = tk; t < T; t++) {
-                own[t] = xdiv(a[t][k], d);
-                if constexpr (VARIANT == 0) {
-                    if (t > tk || r > rk) a[t][k] = own[t];
+                for (int t = tk; t < T; t++) {
+                    num[t] = (t > tk || r > rk) ? a[t][k] : d;
+                    ok &= div_in_range(num[t]);
                 }
+                if (ok) {
+#pragma unroll
+                    for (int t = tk; t < T; t++) own[t] = fast_quotient(num[t], dv);
+                } else {
+#pragma unroll
+                    for (int t = tk; t < T; t++) own[t] = xdiv(num[t], d);
+                }
+            }
+            if constexpr (VARIANT == 0) {
+#pragma unroll
+                for (int t = tk; t < T; t++)
+                    if (t > tk || r > rk) a[t][k] = own[t];
             }
             // all-gather column k (rows k+1 .. N-1) and update
 #pragma unroll

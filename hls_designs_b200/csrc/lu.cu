@@ -336,7 +336,7 @@ lu_rows_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
 // k of U.  Rows that have already served as pivot rows are dead data and are updated along with
 // the live ones (no predication); only their L stores are masked.
 // ------------------------------------------------------------------------------------------------
-template <int N, int R, int WARPS, bool PIVOT>
+template <int N, int R, int WARPS, bool PIVOT, bool ONE_COPY>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restrict__ U, int* __restrict__ P,
                long batch) {
@@ -344,7 +344,7 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
     constexpr int T = N / R;     // data rows per lane
     constexpr int kSlot = N * N + 4;
     constexpr int kPerMat = 2 * kSlot + N;  // floats: A/L slab, U slab, P
-    constexpr uint32_t kMatBytes = N * N * 4;
+    constexpr uint32_t kMatBytes = N * N * 4, kPart = kMatBytes / R;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* base = reinterpret_cast<float*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * MPW * kPerMat * 4);
@@ -368,7 +368,11 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
         __syncwarp();
         if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * kMatBytes);
         __syncwarp();
-        if (m < valid && r == 0) bulk_g2s(sA, A + (m0 + m) * (long)(N * N), kMatBytes, bar);  // one copy per matrix
+        if (ONE_COPY) {
+            if (m < valid && r == 0) bulk_g2s(sA, A + (m0 + m) * (long)(N * N), kMatBytes, bar);
+        } else {
+            if (m < valid) bulk_g2s(sA + r * (kPart / 4), A + (m0 + m) * (long)(N * N) + r * (kPart / 4), kPart, bar);
+        }
         mbar_wait(bar, parity);
         parity ^= 1;
         float a[T][N];
@@ -480,9 +484,14 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
         });
         fence_async_smem();
         __syncwarp();
-        if (m < valid) {  // three stores per matrix, issued by three different lanes of its group
-            if (r == 0) bulk_s2g(L + (m0 + m) * (long)(N * N), sA, kMatBytes);
-            if (r == 1) bulk_s2g(U + (m0 + m) * (long)(N * N), sU, kMatBytes);
+        if (m < valid) {
+            if (ONE_COPY) {  // three stores per matrix, issued by three different lanes of its group
+                if (r == 0) bulk_s2g(L + (m0 + m) * (long)(N * N), sA, kMatBytes);
+                if (r == 1) bulk_s2g(U + (m0 + m) * (long)(N * N), sU, kMatBytes);
+            } else {
+                bulk_s2g(L + (m0 + m) * (long)(N * N) + r * (kPart / 4), sA + r * (kPart / 4), kPart);
+                bulk_s2g(U + (m0 + m) * (long)(N * N) + r * (kPart / 4), sU + r * (kPart / 4), kPart);
+            }
             if (r == R - 1) bulk_s2g(P + (m0 + m) * (long)N, sP, N * 4);
             bulk_commit();
         }
@@ -778,7 +787,9 @@ static cudaError_t launch_lu_regs(const float* A, float* L, float* U, int* P, lo
     constexpr size_t per_warp = (size_t)MPW * (2 * (N * N + 4) + N) * 4;
     static_assert(WARPS * per_warp + WARPS * 8 <= 227 * 1024, "slabs do not fit");
     const size_t smem = WARPS * per_warp + WARPS * sizeof(uint64_t);
-    auto kern = pivoting ? lu_regs_kernel<N, R, WARPS, true> : lu_regs_kernel<N, R, WARPS, false>;
+    // one bulk copy per matrix (ONE_COPY): measured 7-13 % faster here than one part per lane, the opposite of
+    // the HBM-bound Cholesky kernels, which prefer many small copies in flight
+    auto kern = pivoting ? lu_regs_kernel<N, R, WARPS, true, true> : lu_regs_kernel<N, R, WARPS, false, true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long num_slabs = (batch + MPW - 1) / MPW;
