@@ -433,12 +433,22 @@ chol_global_kernel(const float* __restrict__ A, float* __restrict__ L, float* __
 // host-side dispatch
 // ------------------------------------------------------------------------------------------------
 // HLSD_CHOL16 (environment, read once) selects the N=16 kernel for A/B measurements:
-//   "tpm" one thread per matrix (6 warps/SM), "r2" (default) / "r4": 2 / 4 lanes per matrix.
+//   "tpm" one thread per matrix (6 warps/SM), "r2" / "r4" (default): 2 / 4 lanes per matrix
+//   (measured 4739 / 5477 / 6017 GB/s of algorithmic traffic at batch 1M).
 static int chol16_mode() {
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("HLSD_CHOL16");
-        mode = !e ? 2 : (e[0] == 't' ? 1 : (e[1] == '4' ? 4 : 2));
+        mode = !e ? 4 : (e[0] == 't' ? 1 : (e[1] == '2' ? 2 : 4));
+    }
+    return mode;
+}
+
+static int chol_r_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("HLSD_CHOL_R");
+        mode = e ? atoi(e) : 0;
     }
     return mode;
 }
@@ -478,15 +488,21 @@ static cudaError_t launch_tpm(const float* A, float* L, long batch, cudaStream_t
     if constexpr (N == 16) {
         switch (chol16_mode()) {
             case 1: return launch_tpm_w<N, VARIANT, 6>(A, L, batch, st);
-            case 4: return launch_rows<N, 4, VARIANT, 24>(A, L, batch, st);
-            default: return launch_rows<N, 2, VARIANT, 12>(A, L, batch, st);
+            case 2: return launch_rows<N, 2, VARIANT, 12>(A, L, batch, st);
+            default: return launch_rows<N, 4, VARIANT, 24>(A, L, batch, st);
         }
     } else if constexpr (N == 32) {
-        // measured (fraction of HBM peak): 16 lanes per matrix 0.20, 8 lanes 0.30, 4 lanes 0.34: fewer lanes per
-        // matrix mean fewer shuffles per useful operation, even at half the warps per SM
-        return launch_rows<N, 4, VARIANT, 6>(A, L, batch, st);
+        // HLSD_CHOL_R (environment): lanes per matrix for A/B measurements
+        switch (chol_r_mode()) {
+            case 8: return launch_rows<N, 8, VARIANT, 12>(A, L, batch, st);
+            case 16: return launch_rows<N, 16, VARIANT, 24>(A, L, batch, st);
+            default: return launch_rows<N, 4, VARIANT, 6>(A, L, batch, st);
+        }
     } else if constexpr (N == 64) {
-        return launch_rows<N, 32, VARIANT, 12>(A, L, batch, st);  // 16 lanes per matrix measured slower (0.145 vs 0.158)
+        switch (chol_r_mode()) {
+            case 16: return launch_rows<N, 16, VARIANT, 6>(A, L, batch, st);
+            default: return launch_rows<N, 32, VARIANT, 12>(A, L, batch, st);
+        }
     } else {
         return launch_tpm_w<N, VARIANT, 8>(A, L, batch, st);
     }

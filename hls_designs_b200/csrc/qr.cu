@@ -15,9 +15,14 @@
 //
 // Kernels:
 //   qr_tpm_kernel<N>     thread-per-matrix in registers, square N in {4, 8}.
+//   qr_wcols_kernel<N,K> wavefront schedule in registers, K columns of R and K rows of Q per lane, square
+//                        N in {16, 32}, qr_v2.1 arithmetic.
+//   qr_cols_kernel<N>    sequential schedule, lane per column (qr_v1.x arithmetic at N = 16).
 //   qr_wave_kernel<G>    G threads per matrix, R and Q resident in shared memory, wavefront schedule
 //                        (variant 0) or sequential schedule (variant 1).
 //   qr_global_kernel     one CTA per matrix, in place in global memory (any size; exact; slow).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -226,6 +231,140 @@ qr_cols_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// Wavefront in registers (qr_v2.1 arithmetic, square N = 16, 32): C = N / K lanes per matrix, lane l keeps
+// columns l, l + C, ... of R and rows l, l + C, ... of Q (K of each).  The schedule is the wavefront
+// time(i, c) = (N-1-i) + 2c of qr_factor below, fully unrolled, so every row index is a compile-time
+// constant.  The rotations of one step have consecutive columns c, i.e. distinct owner lanes c % C: each
+// owner generates its own angle from its own column, all of them in the same instructions (the systolic
+// arrays' diagonal PEs, qr_v2.1/template/T_qr.cpp:63-148, work side by side in the same way), then every
+// (c, s) is broadcast by shuffle and applied by all lanes of the group to their columns of R to the right
+// of c and to their rows of Q.  Per-element operation order is the sequential loop's: bit-identical.
+// ------------------------------------------------------------------------------------------------
+template <int N, int K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+qr_wcols_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restrict__ R, long batch) {
+    constexpr int C = N / K;     // lanes per matrix
+    constexpr int MPW = 32 / C;  // matrices per warp
+    constexpr int kSlot = N * N + 4;
+    constexpr uint32_t kMatBytes = N * N * 4, kPart = kMatBytes / C;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* slabs = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * MPW * 2 * kSlot * 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int l = lane % C, m = lane / C, gbase = lane - l;
+    float* sR = slabs + ((size_t)warp * MPW + m) * 2 * kSlot;
+    float* sQ = sR + kSlot;
+    uint64_t* bar = bars + warp;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const long num_slabs = (batch + MPW - 1) / MPW;
+    uint32_t parity = 0;
+    for (long sl = (long)blockIdx.x * WARPS + warp; sl < num_slabs; sl += (long)gridDim.x * WARPS) {
+        const long m0 = sl * MPW;
+        const int valid = (int)min((long)MPW, batch - m0);
+        bulk_wait_read<0>();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * kMatBytes);
+        __syncwarp();
+        if (m < valid) bulk_g2s(sR + l * (kPart / 4), A + (m0 + m) * (long)(N * N) + l * (kPart / 4), kPart, bar);
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        float rr[K][N], qq[K][N];
+#pragma unroll
+        for (int kk = 0; kk < K; kk++)
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                rr[kk][i] = sR[i * N + kk * C + l];                 // column kk*C + l of A
+                qq[kk][i] = (i == kk * C + l) ? 1.0f : 0.0f;        // row kk*C + l of the identity
+            }
+        constexpr int kLastStep = (N - 1) + 2 * (N - 2);
+        static_for<0, kLastStep + 1>([&](auto sc) {
+            constexpr int s = decltype(sc)::value;
+            constexpr int c_lo = (s - N + 2) > 0 ? (s - N + 2) : 0;
+            constexpr int c_hi = (s / 2) < (N - 2) ? (s / 2) : (N - 2);
+            constexpr int nrot = c_hi - c_lo + 1;
+            if constexpr (nrot > 0) {
+                static_for<0, (nrot + C - 1) / C>([&](auto chc) {
+                    constexpr int cb = c_lo + decltype(chc)::value * C;
+                    constexpr int cnt = (c_hi - cb + 1) < C ? (c_hi - cb + 1) : C;
+                    // every owner lane picks the generating pair of its own rotation (others: a harmless (1, 1))
+                    float lo = 1.0f, hi = 1.0f;
+                    static_for<0, cnt>([&](auto ec) {
+                        constexpr int c = cb + decltype(ec)::value, i = N - 1 - s + 2 * c;
+                        if (l == c % C) {
+                            lo = rr[c / C][i - 1];
+                            hi = rr[c / C][i];
+                        }
+                    });
+                    // angle generation, all owners at once; a skipped rotation (hi == 0) computes on (1, 1)
+                    const bool skip = givens_skip<0>(hi);
+                    const float x = skip ? 1.0f : hi, y = skip ? 1.0f : lo;
+                    const float mag = xsqrt(xadd(xmul(x, x), xmul(y, y)));
+                    const SharedDivisor dv = make_divisor(mag);
+                    float cs, sn;
+                    if (dv.ok && div_in_range(x) && div_in_range(y)) {
+                        cs = fast_quotient(y, dv);
+                        sn = fast_quotient(x, dv);
+                    } else {
+                        cs = xdiv(y, mag);
+                        sn = xdiv(x, mag);
+                    }
+                    cs = skip ? 1.0f : cs;
+                    sn = skip ? 0.0f : sn;
+                    const float new_lo = skip ? lo : mag, new_hi = skip ? hi : 0.0f;
+                    static_for<0, cnt>([&](auto ec) {
+                        constexpr int c = cb + decltype(ec)::value, i = N - 1 - s + 2 * c;
+                        constexpr int kc = c / C, lc = c % C;
+                        const float cc = __shfl_sync(0xffffffffu, cs, gbase + lc);
+                        const float ss = __shfl_sync(0xffffffffu, sn, gbase + lc);
+                        // R: column kc*C + l takes the rotation when l > lc, is the generating column when l == lc;
+                        // columns of the later groups always take it, earlier ones never
+                        {
+                            const float a0 = rr[kc][i - 1], b0 = rr[kc][i];
+                            float a1 = a0, b1 = b0;
+                            givens_apply(cc, ss, a1, b1);
+                            rr[kc][i - 1] = (l == lc) ? new_lo : (l > lc ? a1 : a0);
+                            rr[kc][i] = (l == lc) ? new_hi : (l > lc ? b1 : b0);
+                        }
+                        static_for<kc + 1, K>([&](auto kkc) {
+                            constexpr int kk = decltype(kkc)::value;
+                            givens_apply(cc, ss, rr[kk][i - 1], rr[kk][i]);
+                        });
+                        static_for<0, K>([&](auto kkc) {
+                            constexpr int kk = decltype(kkc)::value;
+                            givens_apply(cc, ss, qq[kk][i - 1], qq[kk][i]);
+                        });
+                    });
+                });
+            }
+        });
+        __syncwarp();  // every lane has read its columns from the slab
+        if (m < valid) {
+#pragma unroll
+            for (int kk = 0; kk < K; kk++) {
+#pragma unroll
+                for (int i = 0; i < N; i++) sR[i * N + kk * C + l] = rr[kk][i];
+                float4* q4 = reinterpret_cast<float4*>(sQ + (kk * C + l) * N);
+#pragma unroll
+                for (int v = 0; v < N / 4; v++)
+                    q4[v] = make_float4(qq[kk][4 * v], qq[kk][4 * v + 1], qq[kk][4 * v + 2], qq[kk][4 * v + 3]);
+            }
+            fence_async_smem();
+        }
+        __syncwarp();
+        if (m < valid) {
+            bulk_s2g(R + (m0 + m) * (long)(N * N) + l * (kPart / 4), sR + l * (kPart / 4), kPart);
+            bulk_s2g(Q + (m0 + m) * (long)(N * N) + l * (kPart / 4), sQ + l * (kPart / 4), kPart);
+            bulk_commit();
+        }
+    }
+    bulk_wait_read<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
 // shared body: factor one matrix held in r (rows x ldr) / q (rows x ldq) with G threads.
 // cs: scratch for 2 * (rows/2 + 1) floats (the (c, s) pairs of one wavefront).
 // ------------------------------------------------------------------------------------------------
@@ -403,6 +542,30 @@ static cudaError_t launch_qr_cols(const float* A, float* Q, float* R, long batch
     return cudaGetLastError();
 }
 
+template <int N, int K, int WARPS>
+static cudaError_t launch_qr_wcols(const float* A, float* Q, float* R, long batch, cudaStream_t st) {
+    constexpr int MPW = 32 / (N / K);
+    const size_t smem = (size_t)WARPS * MPW * 2 * (N * N + 4) * 4 + WARPS * sizeof(uint64_t);
+    auto kern = qr_wcols_kernel<N, K, WARPS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long num_slabs = (batch + MPW - 1) / MPW;
+    long grid = std::min<long>((num_slabs + WARPS - 1) / WARPS, (long)sm_count());
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(A, Q, R, batch);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// HLSD_QR_REGS=1 (environment): the older kernels for 16x16 / 32x32 (A/B measurements)
+static int qr_regs_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("HLSD_QR_REGS");
+        mode = e ? atoi(e) : 0;
+    }
+    return mode;
+}
+
 static size_t qr_smem_per_matrix(int rows, int cols) {
     return ((size_t)rows * (cols | 1) + (size_t)rows * (rows | 1) + 2 * (rows / 2 + 2)) * 4;
 }
@@ -429,9 +592,16 @@ static cudaError_t qr_dispatch(const float* A, float* Q, float* R, int rows, int
     if (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM) {
         if (aligned && rows == 4 && cols == 4) return launch_qr_tpm<4, VARIANT>(A, Q, R, batch, st);
         if (aligned && rows == 8 && cols == 8) return launch_qr_tpm<8, VARIANT>(A, Q, R, batch, st);
-        if (aligned && rows == 16 && cols == 16) return launch_qr_cols<16, VARIANT>(A, Q, R, batch, st);
-        // (qr_cols_kernel<32> is correct but slower than the wavefront kernel: 16.5 M vs 20.1 M fact/s)
-        if (aligned && rows == 32 && cols == 32 && path == HLSD_PATH_TPM) return launch_qr_cols<32, VARIANT>(A, Q, R, batch, st);
+        // measured (fact/s, batch 1M / 256k): 16x16 K = 1 / 2 / 4 columns per lane 325 M / 463 M / 390 M against 157 M for the
+        // sequential lane-per-column kernel; 32x32 K = 1 / 2 39 M / 42 M against 29 M for the shared-memory wavefront
+        if (aligned && rows == 16 && cols == 16) {
+            if (VARIANT == 0 && qr_regs_mode() == 0) return launch_qr_wcols<16, 2, 16>(A, Q, R, batch, st);
+            return launch_qr_cols<16, VARIANT>(A, Q, R, batch, st);
+        }
+        if (aligned && rows == 32 && cols == 32) {
+            if (VARIANT == 0 && qr_regs_mode() == 0) return launch_qr_wcols<32, 2, 12>(A, Q, R, batch, st);
+            if (path == HLSD_PATH_TPM) return launch_qr_cols<32, VARIANT>(A, Q, R, batch, st);
+        }
         if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
     }
     const size_t per = qr_smem_per_matrix(rows, cols);
