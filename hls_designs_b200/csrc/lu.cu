@@ -336,15 +336,15 @@ lu_rows_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
 // k of U.  Rows that have already served as pivot rows are dead data and are updated along with
 // the live ones (no predication); only their L stores are masked.
 // ------------------------------------------------------------------------------------------------
-template <int N, int R, int WARPS, bool PIVOT, bool ONE_COPY>
+template <int N, int R, int WARPS, bool PIVOT, bool U_DIRECT>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restrict__ U, int* __restrict__ P,
                long batch) {
     constexpr int MPW = 32 / R;  // matrices per warp
     constexpr int T = N / R;     // data rows per lane
     constexpr int kSlot = N * N + 4;
-    constexpr int kPerMat = 2 * kSlot + N;  // floats: A/L slab, U slab, P
-    constexpr uint32_t kMatBytes = N * N * 4, kPart = kMatBytes / R;
+    constexpr int kPerMat = (U_DIRECT ? 1 : 2) * kSlot + N;  // floats: A/L slab, U slab (unless U rows go straight out), P
+    constexpr uint32_t kMatBytes = N * N * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* base = reinterpret_cast<float*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * MPW * kPerMat * 4);
@@ -352,7 +352,7 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
     const int r = lane % R, m = lane / R, gbase = lane - r;
     float* sA = base + ((size_t)warp * MPW + m) * kPerMat;  // operand, then L
     float* sU = sA + kSlot;
-    int* sP = reinterpret_cast<int*>(sU + kSlot);
+    int* sP = reinterpret_cast<int*>(sA + (U_DIRECT ? 1 : 2) * kSlot);
     uint64_t* bar = bars + warp;
     if (lane == 0) {
         mbar_init(bar, 1);
@@ -368,11 +368,7 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
         __syncwarp();
         if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * kMatBytes);
         __syncwarp();
-        if (ONE_COPY) {
-            if (m < valid && r == 0) bulk_g2s(sA, A + (m0 + m) * (long)(N * N), kMatBytes, bar);
-        } else {
-            if (m < valid) bulk_g2s(sA + r * (kPart / 4), A + (m0 + m) * (long)(N * N) + r * (kPart / 4), kPart, bar);
-        }
+        if (m < valid && r == 0) bulk_g2s(sA, A + (m0 + m) * (long)(N * N), kMatBytes, bar);  // one copy per matrix
         mbar_wait(bar, parity);
         parity ^= 1;
         float a[T][N];
@@ -398,7 +394,7 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
                 if (q >= (t * R) / 4 && q >= i / 4)
                     l4[q] = make_float4(i == 4 * q ? 1.0f : 0.0f, i == 4 * q + 1 ? 1.0f : 0.0f, i == 4 * q + 2 ? 1.0f : 0.0f,
                                         i == 4 * q + 3 ? 1.0f : 0.0f);
-                if (q <= (t * R + R - 1) / 4 && q < i / 4) u4[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (!U_DIRECT && q <= (t * R + R - 1) / 4 && q < i / 4) u4[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
         }
         __syncwarp();
@@ -443,8 +439,13 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
                 own[j] = v;
                 u[j] = __shfl_sync(0xffffffffu, v, owner);
             }
-            if (mine) {
-                float4* u4 = reinterpret_cast<float4*>(sU + k * N);
+            if (U_DIRECT ? (mine && m < valid) : mine) {
+                float4* u4 = U_DIRECT ? reinterpret_cast<float4*>(U + (m0 + m) * (long)(N * N) + k * N)
+                                      : reinterpret_cast<float4*>(sU + k * N);
+                if constexpr (U_DIRECT) {
+#pragma unroll
+                    for (int q = 0; q < k / 4; q++) __stcs(u4 + q, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+                }
 #pragma unroll
                 for (int q = k / 4; q < N / 4; q++)
                     u4[q] = make_float4(4 * q >= k ? own[4 * q >= k ? 4 * q : k] : 0.0f,
@@ -485,13 +486,9 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
         fence_async_smem();
         __syncwarp();
         if (m < valid) {
-            if (ONE_COPY) {  // three stores per matrix, issued by three different lanes of its group
-                if (r == 0) bulk_s2g(L + (m0 + m) * (long)(N * N), sA, kMatBytes);
-                if (r == 1) bulk_s2g(U + (m0 + m) * (long)(N * N), sU, kMatBytes);
-            } else {
-                bulk_s2g(L + (m0 + m) * (long)(N * N) + r * (kPart / 4), sA + r * (kPart / 4), kPart);
-                bulk_s2g(U + (m0 + m) * (long)(N * N) + r * (kPart / 4), sU + r * (kPart / 4), kPart);
-            }
+            // one store per matrix and output, issued by different lanes of its group
+            if (r == 0) bulk_s2g(L + (m0 + m) * (long)(N * N), sA, kMatBytes);
+            if (!U_DIRECT && r == 1) bulk_s2g(U + (m0 + m) * (long)(N * N), sU, kMatBytes);
             if (r == R - 1) bulk_s2g(P + (m0 + m) * (long)N, sP, N * 4);
             bulk_commit();
         }
@@ -781,15 +778,15 @@ static cudaError_t launch_lu_rows(const float* A, float* L, float* U, int* P, lo
     return cudaGetLastError();
 }
 
-template <int N, int R, int WARPS>
+template <int N, int R, int WARPS, bool U_DIRECT = false>
 static cudaError_t launch_lu_regs(const float* A, float* L, float* U, int* P, long batch, int pivoting, cudaStream_t st) {
     constexpr int MPW = 32 / R;
-    constexpr size_t per_warp = (size_t)MPW * (2 * (N * N + 4) + N) * 4;
+    constexpr size_t per_warp = (size_t)MPW * ((U_DIRECT ? 1 : 2) * (N * N + 4) + N) * 4;
     static_assert(WARPS * per_warp + WARPS * 8 <= 227 * 1024, "slabs do not fit");
     const size_t smem = WARPS * per_warp + WARPS * sizeof(uint64_t);
-    // one bulk copy per matrix (ONE_COPY): measured 7-13 % faster here than one part per lane, the opposite of
-    // the HBM-bound Cholesky kernels, which prefer many small copies in flight
-    auto kern = pivoting ? lu_regs_kernel<N, R, WARPS, true, true> : lu_regs_kernel<N, R, WARPS, false, true>;
+    // (one bulk copy per matrix: measured 7-13 % faster here than one part per lane, the opposite of the
+    // HBM-bound Cholesky kernels, which prefer many small copies in flight)
+    auto kern = pivoting ? lu_regs_kernel<N, R, WARPS, true, U_DIRECT> : lu_regs_kernel<N, R, WARPS, false, U_DIRECT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long num_slabs = (batch + MPW - 1) / MPW;
@@ -853,13 +850,14 @@ cudaError_t lu_exact(const float* A, float* L, float* U, int* P, int n, long bat
                                   : launch_lu_regs<8, 2, 20>(A, L, U, P, batch, pivoting, st);
         if (aligned && n == 16)
             return lu_mode() == 1 ? launch_lu_rows<16, 4>(A, L, U, P, batch, pivoting, st)
-                                  : launch_lu_regs<16, 4, 12>(A, L, U, P, batch, pivoting, st);
+                                  : launch_lu_regs<16, 4, 12, true>(A, L, U, P, batch, pivoting, st);  // U rows straight out: +10 %
         if (aligned && n == 32)
             return lu_mode() == 1 ? launch_lu_rows<32, 16>(A, L, U, P, batch, pivoting, st)
                  : lu_mode() == 2 ? launch_lu_lane<32>(A, L, U, P, batch, pivoting, st)
                                   : launch_lu_regs<32, 16, 10>(A, L, U, P, batch, pivoting, st);
-        if (aligned && n == 64) return lu_mode() == 1 ? launch_lu_rows<64, 32>(A, L, U, P, batch, pivoting, st)
-                                                       : launch_lu_lane<64>(A, L, U, P, batch, pivoting, st);
+        if (aligned && n == 64)
+            return lu_mode() == 1 ? launch_lu_rows<64, 32>(A, L, U, P, batch, pivoting, st)
+                                  : launch_lu_lane<64>(A, L, U, P, batch, pivoting, st);
         if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
     }
     const size_t per = (size_t)n * (n | 1) * 4;
