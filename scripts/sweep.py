@@ -23,7 +23,9 @@ for kind, sizes in (("chol", (4, 8, 16, 32, 64, 128, 256, 512, 1024)), ("lu", (4
                     ("qr", (4, 8, 16, 32, 64, 128))):
     for n in sizes:
         per = algorithmic_bytes(kind, n, n)
-        batch = int(max(64, min(1 << 20, (3 << 30) // per)))  # ~3 GiB of traffic per step, far beyond L2
+        # ~3 GiB of traffic per step, far beyond L2; the smallest sizes are capped at 8M matrices (a 1M batch of
+        # 4x4 matrices is a 40 us kernel, mostly launch ramp)
+        batch = int(max(64, min(1 << 23, (3 << 30) // per)))
         if kind == "qr" and n >= 64:
             batch = min(batch, 16384)
         if kind == "chol":
