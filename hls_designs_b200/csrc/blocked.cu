@@ -622,11 +622,224 @@ blk_ll_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) 
     if (warp == 0) tmem_dealloc(tmem_d, 128);
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same update with the A operand in TENSOR MEMORY (tcgen05.mma with a TMEM A operand), selected with
+// HLSD_LL_TS=1.  Only B lives in shared memory (per 32-wide chunk 32 KB of writes + 48 KB of MMA reads
+// instead of 64 KB + 96 KB), which lets two CTAs share an SM.  Measured: the same 23.3 ms per batch of
+// 4096 as blk_ll_kernel.  Timing experiments on this kernel (operand loads removed: -4.6 ms, MMAs removed:
+// -1.3 ms, both: -5.6 ms of the update's 8.3 ms) show what bounds both versions: the 44 GB of panel
+// operands that the tiles of one step re-read from L2/HBM (6.3 TB/s), not shared memory and not the
+// tensor pipe.  The next lever is therefore operand reuse (256-row tiles, multicast), not this kernel.
+// Threads 0..127 own the A rows: thread = row keeps its 32 k-values of the chunk in registers
+// (global loads two chunks ahead) and writes them - hi part and lo part - straight into TMEM with
+// tcgen05.st.32x32b.x32 (lane = row, column = k).  Threads 128..255 stage B (raw = hi tile, lo tile)
+// in shared memory as before.  Per chunk: 32 KB of shared-memory writes + 48 KB of MMA reads.
+// TMEM: columns 0..127 accumulator, 128..255 two A buffers of (32 hi + 32 lo) columns.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+struct LlTsSmem {
+    static constexpr int kTile = 128 * 32 * 4;  // one B chunk: 128 rows x 32 k
+    static constexpr int kRaw = 0;              // [2] raw fp32 = tf32 hi operand
+    static constexpr int kLo = 2 * kTile;       // [2] lo operand
+    static constexpr int kBar = 4 * kTile;      // two mbarriers (the epilogue stage reuses the 64 KB below)
+    static constexpr int kTmemPtr = kBar + 16;
+    static constexpr int kTotal = kBar + 32 + 1024;
+};
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+// 256 threads, 64 KB of shared memory, 256 TMEM columns: TWO CTAs per SM, so that one tile's prologue (first
+// loads at full DRAM latency) and epilogue (C tile, TMEM read-out, store) overlap the other's MMAs.
+constexpr int kLlTsThreads = 256;
+
+__global__ void __launch_bounds__(kLlTsThreads, 2)
+blk_ll_ts_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LlTsSmem::kBar);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + LlTsSmem::kTmemPtr);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int r = q + blockIdx.x;
+    float* Lb = L + (long)blockIdx.y * n * n;
+    const float* Sb = S + (long)blockIdx.y * n * n;
+    const float* Arows = Lb + (long)r * NB * n;  // finished panels 0 .. q-1 of block row r
+    const float* Brows = Lb + (long)q * NB * n;  // ... and of block row q
+    const int C = 4 * q;                         // 32-wide K chunks
+
+    if (warp == 0) tmem_alloc(tmem_ptr, 256);
+    if (t == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_ptr;
+
+    const bool a_side = t < 128;  // warp-uniform role
+    // A side (warps 0..3): thread = row = TMEM lane, the 32 k-values of a chunk
+    const float* aptr = Arows + (long)t * n;
+    const uint32_t a_taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + 128u;
+    // B side (warps 4..7): 1024 16-byte pieces per chunk, 8 per thread
+    const int tb = t - 128;
+    float4 buf[2][8];
+    auto gload = [&](int c, float4 (&b)[8]) {
+        if (c < C) {
+            if (a_side) {
+#pragma unroll
+                for (int it = 0; it < 8; it++) b[it] = __ldg(reinterpret_cast<const float4*>(aptr + c * 32) + it);
+            } else {
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                    const int idx = it * 128 + tb, row = idx >> 3, c4 = idx & 7;
+                    b[it] = __ldg(reinterpret_cast<const float4*>(Brows + (long)row * n + c * 32 + c4 * 4));
+                }
+            }
+        }
+    };
+    auto step = [&](int c, float4 (&b)[8]) {
+        if (c >= 2) {  // MMAs of chunk c-2 are done: the TMEM and shared-memory buffers of this parity are free
+            mbar_wait(&bars[c & 1], (uint32_t)(((c - 2) >> 1) & 1));
+            tc_fence_after();
+        }
+        unsigned char* rb = smem + LlTsSmem::kRaw + (c & 1) * LlTsSmem::kTile;
+        unsigned char* lb = smem + LlTsSmem::kLo + (c & 1) * LlTsSmem::kTile;
+        if (a_side) {
+            const uint32_t base = a_taddr + (uint32_t)((c & 1) * 64);
+            uint32_t w[32];
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                w[4 * it] = __float_as_uint(b[it].x) & 0xffffe000u;
+                w[4 * it + 1] = __float_as_uint(b[it].y) & 0xffffe000u;
+                w[4 * it + 2] = __float_as_uint(b[it].z) & 0xffffe000u;
+                w[4 * it + 3] = __float_as_uint(b[it].w) & 0xffffe000u;
+            }
+            tmem_st32(base, w);
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                const float4 l = lo_of(b[it]);
+                w[4 * it] = __float_as_uint(l.x), w[4 * it + 1] = __float_as_uint(l.y);
+                w[4 * it + 2] = __float_as_uint(l.z), w[4 * it + 3] = __float_as_uint(l.w);
+            }
+            tmem_st32(base + 32u, w);
+            gload(c + 2, b);
+            tmem_wait_st();
+        } else {
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                const int idx = it * 128 + tb, row = idx >> 3, c4 = idx & 7;
+                const int off = row * 128 + ((c4 ^ (row & 7)) << 4);
+                *reinterpret_cast<float4*>(rb + off) = b[it];
+                *reinterpret_cast<float4*>(lb + off) = lo_of(b[it]);
+            }
+            gload(c + 2, b);
+            fence_async_smem();
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (t == 0) {
+            const uint64_t dBhi = make_sw128_desc(smem_u32(rb)), dBlo = make_sw128_desc(smem_u32(lb));
+            const uint32_t a_hi = tmem_d + 128u + (uint32_t)((c & 1) * 64), a_lo = a_hi + 32u;
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+                const uint32_t first = (c == 0 && kk == 0) ? 0u : 1u;
+                umma_tf32_ts(tmem_d, a_lo + kk * 8, dBhi + adv, kIdescTf32, first);
+                umma_tf32_ts(tmem_d, a_hi + kk * 8, dBlo + adv, kIdescTf32, 1u);
+                umma_tf32_ts(tmem_d, a_hi + kk * 8, dBhi + adv, kIdescTf32, 1u);
+            }
+            umma_commit(&bars[c & 1]);
+        }
+    };
+    gload(0, buf[0]);
+    gload(1, buf[1]);
+    for (int c = 0; c < C; c += 2) {  // C = 4 q is even
+        step(c, buf[0]);
+        step(c + 1, buf[1]);
+    }
+    // the C tile (from A) is fetched while the last chunks are still being multiplied
+    const long coff = (long)r * NB * n + (long)q * NB;
+    constexpr int kRowsPerWarp = 128 / (kLlTsThreads / 32);
+    float4 cv[kRowsPerWarp];
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; rr++)
+        cv[rr] = *(reinterpret_cast<const float4*>(Sb + coff + (long)(warp * kRowsPerWarp + rr) * n) + lane);
+    mbar_wait(&bars[(C - 2) & 1], (uint32_t)(((C - 2) >> 1) & 1));
+    mbar_wait(&bars[(C - 1) & 1], (uint32_t)(((C - 1) >> 1) & 1));
+    tc_fence_after();
+    {
+        float* stage = reinterpret_cast<float*>(smem);
+        const int drow = (warp & 3) * 32 + lane;  // accumulator row = TMEM lane (warp % 4 selects the lane quarter)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int col = (warp >> 2) * 64 + h * 32;
+            float acc[32];
+            tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col, acc);
+#pragma unroll
+            for (int qq = 0; qq < 8; qq++) {
+                const int c4 = (col >> 2) + qq;
+                *reinterpret_cast<float4*>(stage + drow * 128 + ((c4 ^ (drow & 7)) << 2)) =
+                    make_float4(acc[4 * qq], acc[4 * qq + 1], acc[4 * qq + 2], acc[4 * qq + 3]);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < kRowsPerWarp; rr++) {
+            const int row = warp * kRowsPerWarp + rr;
+            const float4 d = *reinterpret_cast<const float4*>(stage + row * 128 + ((lane ^ (row & 7)) << 2));
+            float4 v = cv[rr];
+            v.x -= d.x, v.y -= d.y, v.z -= d.z, v.w -= d.w;
+            *(reinterpret_cast<float4*>(Lb + coff + (long)row * n) + lane) = v;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, 256);
+}
+
 // left-looking driver: per block column q: update (if q > 0), diagonal block, TRSM
 static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int n, long batch, cudaStream_t st) {
     cudaFuncSetAttribute(blk_mma_kernel<MMA_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
     cudaFuncSetAttribute(blk_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LlSmem::kTotal);
+    cudaFuncSetAttribute(blk_ll_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LlTsSmem::kTotal);
     cudaFuncSetAttribute(blk_diag_kernel<DIAG_CHOL_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
+    static int ll_ts = -1;  // HLSD_LL_TS (environment): 1 = A operand of the update in tensor memory
+    if (ll_ts < 0) {
+        const char* ev = getenv("HLSD_LL_TS");
+        ll_ts = ev ? atoi(ev) : 0;
+    }
     const int panels = n / NB;
     const unsigned nb = (unsigned)batch;
     blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, nb), 256, 0, st>>>(L, n);
@@ -636,7 +849,8 @@ static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int
         const int mt = panels - q - 1;
         const float* src = (q == 0) ? A : L;  // where block column q currently lives
         if (q > 0) {
-            blk_ll_kernel<<<dim3(panels - q, nb), kLlThreads, LlSmem::kTotal, st>>>(A, L, n, q);
+            if (ll_ts) blk_ll_ts_kernel<<<dim3(panels - q, nb), kLlTsThreads, LlTsSmem::kTotal, st>>>(A, L, n, q);
+            else blk_ll_kernel<<<dim3(panels - q, nb), kLlThreads, LlSmem::kTotal, st>>>(A, L, n, q);
             count_launch();
         }
         blk_diag_kernel<DIAG_CHOL_INV><<<nb, 512, kDiagSmem, st>>>(src, L, W, n, o);

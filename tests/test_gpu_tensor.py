@@ -29,6 +29,33 @@ def test_tensor_cholesky_vs_oracle(n, batch):
     assert err < ELEMENT_TOL
 
 
+def test_tensor_cholesky_tmem_operand_variant():
+    """HLSD_LL_TS=1 selects the update kernel that keeps its A operand in tensor memory (read once per process,
+    hence the subprocess); same tolerances."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path[:0] = [%r, %r, %r]\n"
+        "import hls_designs_b200 as hd, restate\n"
+        "from conftest import chol_residual\n"
+        "from hls_designs_b200.operand import gen_spd\n"
+        "for n, batch in ((256, 3), (640, 2), (1024, 1)):\n"
+        "    A = gen_spd(n, batch=batch, seed=n + 1)\n"
+        "    L = hd.cholesky(A, path='tensor')\n"
+        "    want = restate.cholesky(A, threads=8)\n"
+        "    err = np.abs(L - want).max() / np.abs(want).max()\n"
+        "    res = chol_residual(A, L).max()\n"
+        "    assert np.isfinite(L).all() and res < %g and err < %g, (n, res, err)\n"
+        "print('ok')\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
+         os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"), RESIDUAL_TOL, ELEMENT_TOL)
+    env = dict(os.environ, HLSD_LL_TS="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_auto_dispatch_uses_tensor_path_for_large_n():
     A = gen_spd(256, batch=2, seed=9)
     assert np.array_equal(hd.cholesky(A), hd.cholesky(A, path="tensor"))
