@@ -623,13 +623,178 @@ blk_ll_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Two row blocks per CTA: tiles (r0, q) and (r0 + 1, q) share the B operand (block row q), which cuts
+// the panel bytes each step re-reads from L2/HBM by a quarter - the measured bound of the update.
+// Same pipeline as blk_ll_kernel with three operand tiles per chunk (A0, A1, B: raw + lo, double
+// buffered = 192 KB) and two accumulators in TMEM (256 columns).  grid: (ceil((panels - q) / 2), batch)
+// ------------------------------------------------------------------------------------------------
+struct Ll2Smem {
+    static constexpr int kTile = 128 * 32 * 4;
+    static constexpr int kRaw = 0;           // [2 stages][A0, A1, B]
+    static constexpr int kLo = 6 * kTile;    // [2 stages][A0, A1, B]
+    static constexpr int kBar = 12 * kTile;
+    static constexpr int kTmemPtr = kBar + 16;
+    static constexpr int kTotal = kBar + 32 + 1024;
+};
+
+__global__ void __launch_bounds__(512, 1)
+blk_ll2_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Ll2Smem::kBar);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Ll2Smem::kTmemPtr);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int panels = n / NB;
+    const int r0 = q + 2 * blockIdx.x;
+    const bool two = r0 + 1 < panels;  // the last CTA of an odd column holds one tile only
+    float* Lb = L + (long)blockIdx.y * n * n;
+    const float* Sb = S + (long)blockIdx.y * n * n;
+    const float* A0rows = Lb + (long)r0 * NB * n;
+    const float* A1rows = A0rows + (long)NB * n;
+    const float* Brows = Lb + (long)q * NB * n;
+    const bool same = (r0 == q);  // tile 0 is the diagonal tile: B is A0
+    const int C = 4 * q;
+
+    if (warp == 0) tmem_alloc(tmem_ptr, 256);
+    if (t == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_ptr;
+
+    auto piece_off = [&](int it) {
+        const int idx = it * 512 + t, row = idx >> 3, c4 = idx & 7;
+        return row * 128 + ((c4 ^ (row & 7)) << 4);
+    };
+    float4 b0[2][2], b1[2][2], bb[2][2];  // [register stage][piece]: A0, A1, B
+    auto gload = [&](int c, int sreg) {
+        if (c < C) {
+#pragma unroll
+            for (int it = 0; it < 2; it++) {
+                const int idx = it * 512 + t, row = idx >> 3, c4 = idx & 7;
+                const long off = (long)row * n + c * 32 + c4 * 4;
+                b0[sreg][it] = __ldg(reinterpret_cast<const float4*>(A0rows + off));
+                if (two) b1[sreg][it] = __ldg(reinterpret_cast<const float4*>(A1rows + off));
+                if (!same) bb[sreg][it] = __ldg(reinterpret_cast<const float4*>(Brows + off));
+            }
+        }
+    };
+    auto step = [&](int c, int sreg) {
+        if (c >= 2) {
+            mbar_wait(&bars[c & 1], (uint32_t)(((c - 2) >> 1) & 1));
+            tc_fence_after();
+        }
+        unsigned char* ra0 = smem + Ll2Smem::kRaw + (c & 1) * 3 * Ll2Smem::kTile;
+        unsigned char* la0 = smem + Ll2Smem::kLo + (c & 1) * 3 * Ll2Smem::kTile;
+        unsigned char* ra1 = ra0 + Ll2Smem::kTile;
+        unsigned char* la1 = la0 + Ll2Smem::kTile;
+        unsigned char* rb = same ? ra0 : ra0 + 2 * Ll2Smem::kTile;
+        unsigned char* lb = same ? la0 : la0 + 2 * Ll2Smem::kTile;
+#pragma unroll
+        for (int it = 0; it < 2; it++) {
+            const int off = piece_off(it);
+            *reinterpret_cast<float4*>(ra0 + off) = b0[sreg][it];
+            *reinterpret_cast<float4*>(la0 + off) = lo_of(b0[sreg][it]);
+            if (two) {
+                *reinterpret_cast<float4*>(ra1 + off) = b1[sreg][it];
+                *reinterpret_cast<float4*>(la1 + off) = lo_of(b1[sreg][it]);
+            }
+            if (!same) {
+                *reinterpret_cast<float4*>(rb + off) = bb[sreg][it];
+                *reinterpret_cast<float4*>(lb + off) = lo_of(bb[sreg][it]);
+            }
+        }
+        gload(c + 2, sreg);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (t == 0) {
+            const uint64_t dBhi = make_sw128_desc(smem_u32(rb)), dBlo = make_sw128_desc(smem_u32(lb));
+            const uint64_t dA0hi = make_sw128_desc(smem_u32(ra0)), dA0lo = make_sw128_desc(smem_u32(la0));
+            const uint64_t dA1hi = make_sw128_desc(smem_u32(ra1)), dA1lo = make_sw128_desc(smem_u32(la1));
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+                const uint32_t first = (c == 0 && kk == 0) ? 0u : 1u;
+                umma_tf32(tmem_d, dA0lo + adv, dBhi + adv, kIdescTf32, first);
+                umma_tf32(tmem_d, dA0hi + adv, dBlo + adv, kIdescTf32, 1u);
+                umma_tf32(tmem_d, dA0hi + adv, dBhi + adv, kIdescTf32, 1u);
+                if (two) {
+                    umma_tf32(tmem_d + 128u, dA1lo + adv, dBhi + adv, kIdescTf32, first);
+                    umma_tf32(tmem_d + 128u, dA1hi + adv, dBlo + adv, kIdescTf32, 1u);
+                    umma_tf32(tmem_d + 128u, dA1hi + adv, dBhi + adv, kIdescTf32, 1u);
+                }
+            }
+            umma_commit(&bars[c & 1]);
+        }
+    };
+    gload(0, 0);
+    gload(1, 1);
+    for (int c = 0; c < C; c += 2) {  // C = 4 q is even
+        step(c, 0);
+        step(c + 1, 1);
+    }
+    // the C tiles (from A) are fetched while the last chunks are still being multiplied
+    const long coff = (long)r0 * NB * n + (long)q * NB;
+    constexpr int kRowsPerWarp = 8;
+    float4 cv[2][kRowsPerWarp];
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+        if (h == 0 || two) {
+#pragma unroll
+            for (int rr = 0; rr < kRowsPerWarp; rr++)
+                cv[h][rr] = *(reinterpret_cast<const float4*>(Sb + coff + (long)(h * NB + warp * kRowsPerWarp + rr) * n) + lane);
+        }
+    mbar_wait(&bars[(C - 2) & 1], (uint32_t)(((C - 2) >> 1) & 1));
+    mbar_wait(&bars[(C - 1) & 1], (uint32_t)(((C - 1) >> 1) & 1));
+    tc_fence_after();
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        if (h == 1 && !two) break;
+        float* stage = reinterpret_cast<float*>(smem) + h * (128 * 128);
+        const int drow = (warp & 3) * 32 + lane;
+        const int col = (warp >> 2) * 32;
+        float acc[32];
+        tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(h * 128 + col), acc);
+#pragma unroll
+        for (int qq = 0; qq < 8; qq++) {
+            const int c4 = (col >> 2) + qq;
+            *reinterpret_cast<float4*>(stage + drow * 128 + ((c4 ^ (drow & 7)) << 2)) =
+                make_float4(acc[4 * qq], acc[4 * qq + 1], acc[4 * qq + 2], acc[4 * qq + 3]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        if (h == 1 && !two) break;
+        const float* stage = reinterpret_cast<const float*>(smem) + h * (128 * 128);
+#pragma unroll
+        for (int rr = 0; rr < kRowsPerWarp; rr++) {
+            const int row = warp * kRowsPerWarp + rr;
+            const float4 d = *reinterpret_cast<const float4*>(stage + row * 128 + ((lane ^ (row & 7)) << 2));
+            float4 v = cv[h][rr];
+            v.x -= d.x, v.y -= d.y, v.z -= d.z, v.w -= d.w;
+            *(reinterpret_cast<float4*>(Lb + coff + (long)(h * NB + row) * n) + lane) = v;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
 // The same update with the A operand in TENSOR MEMORY (tcgen05.mma with a TMEM A operand), selected with
 // HLSD_LL_TS=1.  Only B lives in shared memory (per 32-wide chunk 32 KB of writes + 48 KB of MMA reads
 // instead of 64 KB + 96 KB), which lets two CTAs share an SM.  Measured: the same 23.3 ms per batch of
 // 4096 as blk_ll_kernel.  Timing experiments on this kernel (operand loads removed: -4.6 ms, MMAs removed:
 // -1.3 ms, both: -5.6 ms of the update's 8.3 ms) show what bounds both versions: the 44 GB of panel
 // operands that the tiles of one step re-read from L2/HBM (6.3 TB/s), not shared memory and not the
-// tensor pipe.  The next lever is therefore operand reuse (256-row tiles, multicast), not this kernel.
+// tensor pipe.  The lever is therefore operand reuse: blk_ll2_kernel above (two row blocks per CTA).
 // Threads 0..127 own the A rows: thread = row keeps its 32 k-values of the chunk in registers
 // (global loads two chunks ahead) and writes them - hi part and lo part - straight into TMEM with
 // tcgen05.st.32x32b.x32 (lane = row, column = k).  Threads 128..255 stage B (raw = hi tile, lo tile)
@@ -834,11 +999,15 @@ static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int
     cudaFuncSetAttribute(blk_mma_kernel<MMA_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
     cudaFuncSetAttribute(blk_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LlSmem::kTotal);
     cudaFuncSetAttribute(blk_ll_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LlTsSmem::kTotal);
+    cudaFuncSetAttribute(blk_ll2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Ll2Smem::kTotal);
     cudaFuncSetAttribute(blk_diag_kernel<DIAG_CHOL_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
-    static int ll_ts = -1;  // HLSD_LL_TS (environment): 1 = A operand of the update in tensor memory
+    // HLSD_LL_TS (environment): update kernel variant.  2 (default) = two row blocks per CTA, 0 = one tile per
+    // CTA, 1 = one tile per CTA with the A operand in tensor memory.  Measured per batch of 4096 1024x1024
+    // matrices: 21.5 / 23.3 / 23.3 ms.
+    static int ll_ts = -1;
     if (ll_ts < 0) {
         const char* ev = getenv("HLSD_LL_TS");
-        ll_ts = ev ? atoi(ev) : 0;
+        ll_ts = ev ? atoi(ev) : 2;
     }
     const int panels = n / NB;
     const unsigned nb = (unsigned)batch;
@@ -849,7 +1018,8 @@ static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int
         const int mt = panels - q - 1;
         const float* src = (q == 0) ? A : L;  // where block column q currently lives
         if (q > 0) {
-            if (ll_ts) blk_ll_ts_kernel<<<dim3(panels - q, nb), kLlTsThreads, LlTsSmem::kTotal, st>>>(A, L, n, q);
+            if (ll_ts == 1) blk_ll_ts_kernel<<<dim3(panels - q, nb), kLlTsThreads, LlTsSmem::kTotal, st>>>(A, L, n, q);
+            else if (ll_ts == 2) blk_ll2_kernel<<<dim3((panels - q + 1) / 2, nb), 512, Ll2Smem::kTotal, st>>>(A, L, n, q);
             else blk_ll_kernel<<<dim3(panels - q, nb), kLlThreads, LlSmem::kTotal, st>>>(A, L, n, q);
             count_launch();
         }
