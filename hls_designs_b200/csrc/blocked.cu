@@ -1255,9 +1255,11 @@ __device__ __forceinline__ PivCand piv_better(PivCand a, PivCand b) {
 // the panel, at least 256 because threads 0..191 also serve as column workers between sub-panels).
 __global__ void __launch_bounds__(1024, 1)
 lu_panel_kernel(float* __restrict__ Wk, float* __restrict__ L, int* __restrict__ P, int n, int o) {
-    __shared__ float urow[32];       // pivot row, columns kk.. of the sub-panel
-    __shared__ float krow[32];       // the row that sat at position k before the exchange
-    __shared__ PivCand red[32];
+    // double buffered by column parity: two barriers per column are enough (after the search partials, after the
+    // pivot row is published); a warp that runs ahead into the next column writes the other buffers
+    __shared__ float urow_b[2][32];  // pivot row, columns kk.. of the sub-panel
+    __shared__ float krow_b[2][32];  // the row that sat at position k before the exchange
+    __shared__ PivCand red_b[2][32];
     __shared__ int spiv[32];         // pivots of the current sub-panel (absolute row indices)
     __shared__ float l11[32][33];    // multipliers of the sub-panel's own 32 rows
     __shared__ __align__(16) float ublk[32][96];  // U rows of the sub-panel for the columns right of it
@@ -1286,7 +1288,10 @@ lu_panel_kernel(float* __restrict__ Wk, float* __restrict__ L, int* __restrict__
             constexpr int kk = decltype(kkc)::value;
             const int k = cs + kk;  // pivot position (absolute row = absolute column)
             int p = k;
+            float* urow = urow_b[kk & 1];
+            float* krow = krow_b[kk & 1];
             if (k < n - 1) {
+                PivCand* red = red_b[kk & 1];
                 PivCand c{-2.0f, 0x7fffffff};
                 if (live && row >= k) {
                     float v = fabsf(a[kk]);
@@ -1300,24 +1305,18 @@ lu_panel_kernel(float* __restrict__ Wk, float* __restrict__ L, int* __restrict__
                 }
                 if (lane == 0) red[warp] = c;
                 __syncthreads();
-                if (warp == 0) {
-                    PivCand c2 = lane < (int)(blockDim.x >> 5) ? red[lane] : PivCand{-2.0f, 0x7fffffff};
+                // every warp reduces the per-warp candidates itself (no second barrier, no broadcast)
+                PivCand c2 = lane < (int)(blockDim.x >> 5) ? red[lane] : PivCand{-2.0f, 0x7fffffff};
 #pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) {
-                        PivCand o2{__shfl_xor_sync(0xffffffffu, c2.v, off), __shfl_xor_sync(0xffffffffu, c2.i, off)};
-                        c2 = piv_better(c2, o2);
-                    }
-                    if (lane == 0) {
-                        red[0] = c2;
-                        spiv[kk] = c2.i;
-                        pv[k] = c2.i;
-                    }
+                for (int off = 16; off > 0; off >>= 1) {
+                    PivCand o2{__shfl_xor_sync(0xffffffffu, c2.v, off), __shfl_xor_sync(0xffffffffu, c2.i, off)};
+                    c2 = piv_better(c2, o2);
                 }
-                __syncthreads();
-                p = red[0].i;
-            } else if (t == 0) {
-                spiv[kk] = k;
-                pv[k] = k;
+                p = c2.i;
+            }
+            if (t == 0) {
+                spiv[kk] = p;
+                pv[k] = p;
             }
             // whole rows are exchanged (multipliers included, LAPACK style: the deferred block updates below
             // need L in final row order; lu_unswap_panel_kernel restores the reference's convention afterwards)
@@ -1345,7 +1344,6 @@ lu_panel_kernel(float* __restrict__ Wk, float* __restrict__ L, int* __restrict__
 #pragma unroll
                 for (int j = kk + 1; j < 32; j++) a[j] = fmaf(-l, urow[j], a[j]);
             }
-            __syncthreads();  // urow / krow / red are reused by the next column
         });
         // write the sub-panel: multipliers to L (unit diagonal, zeros above), U11 entries to the working matrix
         if (live) {
