@@ -5,7 +5,7 @@
 // tests), so one arithmetic serves the three designs.  `pivoting == 0` skips the search (P[k] = k).
 //
 // Kernels:
-//   lu_tpm_kernel<N>      thread-per-matrix in registers, N = 4 (and 8 for A/B runs): staged slabs.
+//   lu_tpm_kernel<N>      thread-per-matrix in registers, N = 4: staged slabs.
 //   lu_regs_kernel<N,R>   R lanes per matrix, all in registers, N in {8, 16, 32}: pivot row by shuffle.
 //   lu_lane_kernel<N>     one lane per row, N = 64 (two warps per matrix).
 //   lu_group_kernel<G>    G threads per matrix, matrix resident in shared memory.
@@ -157,183 +157,20 @@ lu_tpm_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// R lanes per matrix, rows in registers (N = 16, 32, 64): lane r of a group owns data rows r + R t,
-// each a full row of N registers.  Rows are never moved: every data row carries its current
-// position pos[t]; a pivot exchange swaps two positions.  Column blocks of 8: at the start of block
-// KB every lane parks its rows' 8 block columns in a private shared-memory strip (the step index
-// inside a block is a run-time value and registers cannot be indexed by it), the remaining columns
-// stay in registers and are only ever indexed by compile-time constants.  Per step k:
+// R lanes per matrix, everything in registers (N = 8, 16, 32): lane r of a group owns data rows
+// r + R t, each a full row of N registers; the step loop is unrolled at compile time, so registers are
+// only ever indexed by constants.  Rows are never moved: every data row carries its current position
+// pos[t]; a pivot exchange swaps two positions.  Per step k:
 //   pivot search   each lane offers (|a_ik|, position) of its rows still below the pivot; butterfly
 //                  arg-max over the group with the reference's tie rule (smallest position wins)
-//   pivot row      its owner writes it to row k of the U slab (the systolic "pivot broadcast")
+//   pivot row      its owner lane (found by a ballot over the group) selects it from its T rows and
+//                  broadcasts it column by column by shuffle (the systolic "pivot broadcast"); the
+//                  owner also stores it as row k of U
 //   column / update  every lane divides its entries of column k by the pivot, stores them into the
 //                  L slab at the rows' current positions, and subtracts l_ik * u_kj from its rows
-// L (unit lower) and U (upper) are assembled in two shared-memory slabs and leave by bulk stores.
-// Operation order per element is the reference's (k ascending, separate roundings): bit-identical.
-// ------------------------------------------------------------------------------------------------
-template <int N, int R, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1)
-lu_rows_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restrict__ U, int* __restrict__ P,
-               long batch, int pivoting) {
-    constexpr int MPW = 32 / R;   // matrices per warp
-    constexpr int T = N / R;      // data rows per lane
-    constexpr int kSlot = N * N + 4;
-    constexpr int kStrip = T * 8 + 1;  // floats of panel strip per lane (odd: lanes fall on distinct banks)
-    constexpr int kStripAll = (R * kStrip + 3) / 4 * 4;  // keep what follows 16-byte aligned
-    constexpr int kPerMat = 2 * kSlot + kStripAll + N;  // floats: A/L slab, U slab, strips, P
-    constexpr uint32_t kMatBytes = N * N * 4, kPart = kMatBytes / R;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* base = reinterpret_cast<float*>(smem_raw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * MPW * kPerMat * 4);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = lane % R, m = lane / R;
-    float* sA = base + ((size_t)warp * MPW + m) * kPerMat;  // operand, then L
-    float* sU = sA + kSlot;
-    float* sp = sU + kSlot + r * kStrip;                      // this lane's strip: sp[t * 8 + q]
-    int* sP = reinterpret_cast<int*>(sU + kSlot + kStripAll);
-    uint64_t* bar = bars + warp;
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        fence_mbar_init();
-    }
-    __syncwarp();
-    const long num_slabs = (batch + MPW - 1) / MPW;
-    uint32_t parity = 0;
-    for (long s = (long)blockIdx.x * WARPS + warp; s < num_slabs; s += (long)gridDim.x * WARPS) {
-        const long m0 = s * MPW;
-        const int valid = (int)min((long)MPW, batch - m0);
-        bulk_wait_read<0>();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * kMatBytes);
-        __syncwarp();
-        if (m < valid && r == 0) bulk_g2s(sA, A + (m0 + m) * (long)(N * N), kMatBytes, bar);  // one copy per matrix
-        mbar_wait(bar, parity);
-        parity ^= 1;
-        float a[T][N];
-        int pos[T];
-#pragma unroll
-        for (int t = 0; t < T; t++) {
-            pos[t] = t * R + r;
-            const float4* row4 = reinterpret_cast<const float4*>(sA + (t * R + r) * N);
-#pragma unroll
-            for (int q = 0; q < N / 4; q++) {
-                float4 v = row4[q];
-                a[t][4 * q] = v.x, a[t][4 * q + 1] = v.y, a[t][4 * q + 2] = v.z, a[t][4 * q + 3] = v.w;
-            }
-        }
-        __syncwarp();  // the operand is in registers: the slab becomes L (identity), the other U (zero)
-#pragma unroll
-        for (int t = 0; t < T; t++) {
-            const int i = t * R + r;
-            float4* l4 = reinterpret_cast<float4*>(sA + i * N);
-            float4* u4 = reinterpret_cast<float4*>(sU + i * N);
-#pragma unroll
-            for (int q = 0; q < N / 4; q++) {
-                l4[q] = make_float4(i == 4 * q ? 1.0f : 0.0f, i == 4 * q + 1 ? 1.0f : 0.0f, i == 4 * q + 2 ? 1.0f : 0.0f,
-                                    i == 4 * q + 3 ? 1.0f : 0.0f);
-                u4[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            }
-        }
-        __syncwarp();
-        static_for<0, N / 8>([&](auto kbc) {
-            constexpr int KB = decltype(kbc)::value;
-            constexpr int c0 = 8 * KB;  // first column of the block; registers serve columns >= c0 + 8
-#pragma unroll
-            for (int t = 0; t < T; t++)
-#pragma unroll
-                for (int q = 0; q < 8; q++) sp[t * 8 + q] = a[t][c0 + q];
-            for (int kr = 0; kr < 8; kr++) {
-                const int k = c0 + kr;
-                int p = k;
-                if (pivoting && k < N - 1) {
-                    PivotCand c{-2.0f, 0x7fffffff};
-#pragma unroll
-                    for (int t = 0; t < T; t++)
-                        if (pos[t] >= k) c = pivot_better(c, PivotCand{pivot_key(sp[t * 8 + kr], pos[t] == k), pos[t]});
-#pragma unroll
-                    for (int off = R / 2; off > 0; off >>= 1) {
-                        PivotCand o{__shfl_xor_sync(0xffffffffu, c.v, off), __shfl_xor_sync(0xffffffffu, c.i, off)};
-                        c = pivot_better(c, o);
-                    }
-                    p = c.i;
-                }
-                if (r == 0) sP[k] = p;
-                bool isp[T];
-                bool mine = false;
-#pragma unroll
-                for (int t = 0; t < T; t++) {
-                    if (pos[t] == p) pos[t] = k;
-                    else if (pos[t] == k) pos[t] = p;
-                    isp[t] = pos[t] == k;
-                    mine |= isp[t];
-                }
-                // pivot row -> row k of U (columns >= k)
-                {
-                    float* urow = sU + k * N;
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        float v = sp[q];
-#pragma unroll
-                        for (int t = 1; t < T; t++) v = isp[t] ? sp[t * 8 + q] : v;
-                        if (mine && q >= kr) urow[c0 + q] = v;
-                    }
-#pragma unroll
-                    for (int j = c0 + 8; j < N; j += 4) {
-                        float4 v = make_float4(a[0][j], a[0][j + 1], a[0][j + 2], a[0][j + 3]);
-#pragma unroll
-                        for (int t = 1; t < T; t++)
-                            if (isp[t]) v = make_float4(a[t][j], a[t][j + 1], a[t][j + 2], a[t][j + 3]);
-                        if (mine) *reinterpret_cast<float4*>(urow + j) = v;
-                    }
-                }
-                __syncwarp();
-                const float* urow = sU + k * N;
-                const float piv = urow[k];
-                float lm[T];
-                bool act[T];
-#pragma unroll
-                for (int t = 0; t < T; t++) {
-                    act[t] = pos[t] > k;
-                    lm[t] = 0.0f;
-                    if (act[t]) {
-                        lm[t] = xdiv(sp[t * 8 + kr], piv);
-                        sA[pos[t] * N + k] = lm[t];
-                        for (int q = kr + 1; q < 8; q++) sp[t * 8 + q] = xmsub(sp[t * 8 + q], lm[t], urow[c0 + q]);
-                    }
-                }
-#pragma unroll
-                for (int j = c0 + 8; j < N; j += 4) {
-                    const float4 u = *reinterpret_cast<const float4*>(urow + j);
-#pragma unroll
-                    for (int t = 0; t < T; t++)
-                        if (act[t]) {
-                            a[t][j] = xmsub(a[t][j], lm[t], u.x);
-                            a[t][j + 1] = xmsub(a[t][j + 1], lm[t], u.y);
-                            a[t][j + 2] = xmsub(a[t][j + 2], lm[t], u.z);
-                            a[t][j + 3] = xmsub(a[t][j + 3], lm[t], u.w);
-                        }
-                }
-                __syncwarp();
-            }
-        });
-        fence_async_smem();
-        __syncwarp();
-        if (m < valid) {
-            bulk_s2g(L + (m0 + m) * (long)(N * N) + r * (kPart / 4), sA + r * (kPart / 4), kPart);
-            bulk_s2g(U + (m0 + m) * (long)(N * N) + r * (kPart / 4), sU + r * (kPart / 4), kPart);
-            if (r == 0) bulk_s2g(P + (m0 + m) * (long)N, sP, N * 4);
-            bulk_commit();
-        }
-    }
-    bulk_wait_read<0>();
-}
-
-// ------------------------------------------------------------------------------------------------
-// R lanes per matrix, everything in registers (N = 8, 16, 32): as lu_rows_kernel, but the step loop
-// is unrolled at compile time, so no column ever needs a run-time register index and the strips
-// disappear.  The pivot row travels by shuffle: its owner lane (found by a ballot over the group)
-// selects it from its T rows and broadcasts it column by column; the owner also stores it as row
-// k of U.  Rows that have already served as pivot rows are dead data and are updated along with
+// L (unit lower) is assembled in a shared-memory slab and leaves by a bulk store; so does U unless
+// U_DIRECT.  Operation order per element is the reference's (k ascending, separate roundings):
+// bit-identical.  Rows that have already served as pivot rows are dead data and are updated along with
 // the live ones (no predication); only their L stores are masked.
 // ------------------------------------------------------------------------------------------------
 template <int N, int R, int WARPS, bool PIVOT, bool U_DIRECT>
@@ -497,9 +334,10 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// One lane per row (N = 32: one warp per matrix, N = 64: two warps per matrix): the same scheme as
-// lu_rows_kernel with a single data row per lane, which removes the per-lane row selection from the
-// pivot-row broadcast and halves the register tile.  Two barriers per column (after the pivot
+// One lane per row (N = 64: two warps per matrix; N = 32 would be one): position tracking as in
+// lu_regs_kernel with a single data row per lane; the 8 columns of the current block live in a per-lane
+// shared-memory strip (the step index inside a block is a run-time value here and registers cannot be
+// indexed by it), the pivot row is published through shared memory.  Two barriers per column (after the pivot
 // search partials, after the pivot row is published), named barriers for the two-warp case.
 // ------------------------------------------------------------------------------------------------
 template <int N, int MATS>
@@ -761,23 +599,6 @@ static cudaError_t launch_lu_tpm(const float* A, float* L, float* U, int* P, lon
     return cudaGetLastError();
 }
 
-template <int N, int R>
-static cudaError_t launch_lu_rows(const float* A, float* L, float* U, int* P, long batch, int pivoting, cudaStream_t st) {
-    constexpr int MPW = 32 / R, T = N / R;
-    constexpr size_t per_warp = (size_t)MPW * (2 * (N * N + 4) + (R * (T * 8 + 1) + 3) / 4 * 4 + N) * 4;
-    constexpr int WARPS = (int)((227 * 1024 - 1024) / per_warp) < 12 ? (int)((227 * 1024 - 1024) / per_warp) : 12;
-    static_assert(WARPS >= 1, "matrix does not fit");
-    const size_t smem = WARPS * per_warp + WARPS * sizeof(uint64_t);
-    auto kern = lu_rows_kernel<N, R, WARPS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const long num_slabs = (batch + MPW - 1) / MPW;
-    long grid = std::min<long>((num_slabs + WARPS - 1) / WARPS, (long)sm_count());
-    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(A, L, U, P, batch, pivoting);
-    count_launch();
-    return cudaGetLastError();
-}
-
 template <int N, int R, int WARPS, bool U_DIRECT = false>
 static cudaError_t launch_lu_regs(const float* A, float* L, float* U, int* P, long batch, int pivoting, cudaStream_t st) {
     constexpr int MPW = 32 / R;
@@ -828,36 +649,16 @@ static cudaError_t launch_lu_group(const float* A, float* L, float* U, int* P, i
     return cudaGetLastError();
 }
 
-// HLSD_LU_ROWS (environment): older kernel variants for A/B measurements, see lu_exact
-static int lu_mode() {
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("HLSD_LU_ROWS");
-        mode = e ? atoi(e) : 0;
-    }
-    return mode;
-}
-
 cudaError_t lu_exact(const float* A, float* L, float* U, int* P, int n, long batch, int pivoting, int path,
                      cudaStream_t st) {
     if (batch == 0) return cudaSuccess;
     const bool aligned = (((uintptr_t)A | (uintptr_t)L | (uintptr_t)U | (uintptr_t)P) & 15) == 0;
     if (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM) {
         if (aligned && n == 4) return launch_lu_tpm<4>(A, L, U, P, batch, pivoting, st);
-        // HLSD_LU_ROWS selects the older kernels for A/B measurements (1: strips in shared memory, 2: one lane per row)
-        if (aligned && n == 8)
-            return lu_mode() == 1 ? launch_lu_tpm<8>(A, L, U, P, batch, pivoting, st)
-                                  : launch_lu_regs<8, 2, 20>(A, L, U, P, batch, pivoting, st);
-        if (aligned && n == 16)
-            return lu_mode() == 1 ? launch_lu_rows<16, 4>(A, L, U, P, batch, pivoting, st)
-                                  : launch_lu_regs<16, 4, 12, true>(A, L, U, P, batch, pivoting, st);  // U rows straight out: +10 %
-        if (aligned && n == 32)
-            return lu_mode() == 1 ? launch_lu_rows<32, 16>(A, L, U, P, batch, pivoting, st)
-                 : lu_mode() == 2 ? launch_lu_lane<32>(A, L, U, P, batch, pivoting, st)
-                                  : launch_lu_regs<32, 16, 10>(A, L, U, P, batch, pivoting, st);
-        if (aligned && n == 64)
-            return lu_mode() == 1 ? launch_lu_rows<64, 32>(A, L, U, P, batch, pivoting, st)
-                                  : launch_lu_lane<64>(A, L, U, P, batch, pivoting, st);
+        if (aligned && n == 8) return launch_lu_regs<8, 2, 20>(A, L, U, P, batch, pivoting, st);
+        if (aligned && n == 16) return launch_lu_regs<16, 4, 12, true>(A, L, U, P, batch, pivoting, st);  // U rows straight out: +10 %
+        if (aligned && n == 32) return launch_lu_regs<32, 16, 10>(A, L, U, P, batch, pivoting, st);
+        if (aligned && n == 64) return launch_lu_lane<64>(A, L, U, P, batch, pivoting, st);
         if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
     }
     const size_t per = (size_t)n * (n | 1) * 4;
