@@ -334,22 +334,21 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// One lane per row (N = 64: two warps per matrix; N = 32 would be one): position tracking as in
-// lu_regs_kernel with a single data row per lane; the 8 columns of the current block live in a per-lane
-// shared-memory strip (the step index inside a block is a run-time value here and registers cannot be
-// indexed by it), the pivot row is published through shared memory.  Two barriers per column (after the pivot
-// search partials, after the pivot row is published), named barriers for the two-warp case.
+// One lane per row (N = 64: two warps per matrix): position tracking as in lu_regs_kernel with a
+// single data row per lane, the step loop unrolled at compile time.  The pivot row is published
+// through a double-buffered shared-memory row (its owner also stores it straight to global memory as
+// row k of U); the per-warp search partials of the two warps meet in shared memory.  Two named
+// barriers per column (after the partials, after the pivot row); the butterfly of the next column's
+// search is issued right after that column is updated and overlaps the rest of the update.
 // ------------------------------------------------------------------------------------------------
-template <int N, int MATS>
+template <int N, int MATS, bool PIVOT>
 __global__ void __launch_bounds__(MATS * N, 1)
 lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restrict__ U, int* __restrict__ P,
-               long batch, int pivoting) {
+               long batch) {
     static_assert(N == 32 || N == 64, "one or two warps per matrix");
     constexpr int WPM = N / 32;  // warps per matrix
     constexpr int kSlot = N * N + 4;
-    constexpr int kStrip = 9;    // 8 block columns + 1: lanes fall on distinct banks
-    constexpr int kStripAll = (N * kStrip + 3) / 4 * 4;
-    constexpr int kPerMat = kSlot + 2 * N + kStripAll + N + 8;  // floats: A/L slab, 2 pivot-row buffers, strips, P, partials
+    constexpr int kPerMat = kSlot + 2 * N + N + 8;  // floats: A/L slab, 2 pivot-row buffers, P, partials
     constexpr uint32_t kRowBytes = N * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* base = reinterpret_cast<float*>(smem_raw);
@@ -357,8 +356,7 @@ lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
     const int mat = threadIdx.x / N, r = threadIdx.x % N, lane = threadIdx.x & 31;
     float* sA = base + (size_t)mat * kPerMat;
     float* sRow = sA + kSlot;  // [2][N]: the pivot row of step k in buffer k & 1
-    float* sp = sRow + 2 * N + r * kStrip;
-    int* sP = reinterpret_cast<int*>(sRow + 2 * N + kStripAll);
+    int* sP = reinterpret_cast<int*>(sRow + 2 * N);
     PivotCand* part = reinterpret_cast<PivotCand*>(sP + N);  // [2 parities][WPM]
     uint64_t* bar = bars + mat;
     auto gsync = [&]() {
@@ -399,68 +397,74 @@ lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
         float* ug = U + b * (long)(N * N);  // U rows go straight to global memory, one finished row per step
         int pos = r;
         gsync();
-        static_for<0, N / 8>([&](auto kbc) {
-            constexpr int KB = decltype(kbc)::value;
-            constexpr int c0 = 8 * KB;
+        // this warp's best candidate of column k (rows at positions >= k)
+        auto search = [&](auto kc) -> PivotCand {
+            constexpr int k = decltype(kc)::value;
+            PivotCand c{-2.0f, 0x7fffffff};
+            if constexpr (PIVOT && k < N - 1) {
+                if (pos >= k) c = PivotCand{pivot_key(a[k], pos == k), pos};
 #pragma unroll
-            for (int q = 0; q < 8; q++) sp[q] = a[c0 + q];
-            for (int kr = 0; kr < 8; kr++) {
-                const int k = c0 + kr;
-                int p = k;
-                if (pivoting && k < N - 1) {
-                    PivotCand c{-2.0f, 0x7fffffff};
-                    if (pos >= k) c = PivotCand{pivot_key(sp[kr], pos == k), pos};
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) {
-                        PivotCand o{__shfl_xor_sync(0xffffffffu, c.v, off), __shfl_xor_sync(0xffffffffu, c.i, off)};
-                        c = pivot_better(c, o);
-                    }
-                    if constexpr (WPM == 2) {
-                        PivotCand* pp = part + (k & 1) * 2;
-                        if (lane == 0) pp[r >> 5] = c;
-                        gsync();
-                        c = pivot_better(pp[0], pp[1]);
-                    }
-                    p = c.i;
+                for (int off = 16; off > 0; off >>= 1) {
+                    PivotCand o{__shfl_xor_sync(0xffffffffu, c.v, off), __shfl_xor_sync(0xffffffffu, c.i, off)};
+                    c = pivot_better(c, o);
                 }
-                if (r == 0) sP[k] = p;
-                if (pos == p) pos = k;
-                else if (pos == k) pos = p;
-                float* urow = sRow + (k & 1) * N;
-                if (pos == k) {  // this lane holds the pivot row: publish columns >= k and store row k of U
-                    float4* ug4 = reinterpret_cast<float4*>(ug + k * N);
-#pragma unroll
-                    for (int j = 0; j < c0; j += 4) __stcs(ug4 + j / 4, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
-                    float blkv[8];
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        blkv[q] = (q >= kr) ? sp[q] : 0.0f;
-                        urow[c0 + q] = blkv[q];
-                    }
-                    __stcs(ug4 + c0 / 4, make_float4(blkv[0], blkv[1], blkv[2], blkv[3]));
-                    __stcs(ug4 + c0 / 4 + 1, make_float4(blkv[4], blkv[5], blkv[6], blkv[7]));
-#pragma unroll
-                    for (int j = c0 + 8; j < N; j += 4) {
-                        const float4 v4 = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
-                        *reinterpret_cast<float4*>(urow + j) = v4;
-                        __stcs(ug4 + j / 4, v4);
-                    }
+            }
+            return c;
+        };
+        PivotCand cand = search(std::integral_constant<int, 0>{});
+        static_for<0, N>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            int p = k;
+            if constexpr (PIVOT && k < N - 1) {
+                if constexpr (WPM == 2) {
+                    PivotCand* pp = part + (k & 1) * 2;
+                    if (lane == 0) pp[r >> 5] = cand;
+                    gsync();
+                    cand = pivot_better(pp[0], pp[1]);
                 }
-                gsync();
-                if (pos > k) {
-                    const float lm = xdiv(sp[kr], urow[k]);
-                    sA[pos * N + k] = lm;
-                    for (int q = kr + 1; q < 8; q++) sp[q] = xmsub(sp[q], lm, urow[c0 + q]);
+                p = cand.i;
+            }
+            if (r == 0) sP[k] = p;
+            if (pos == p) pos = k;
+            else if (pos == k) pos = p;
+            float* urow = sRow + (k & 1) * N;
+            if (pos == k) {  // this lane holds the pivot row: publish columns >= k and store row k of U
+                float4* ug4 = reinterpret_cast<float4*>(ug + k * N);
+                float4* ur4 = reinterpret_cast<float4*>(urow);
 #pragma unroll
-                    for (int j = c0 + 8; j < N; j += 4) {
-                        const float4 u = *reinterpret_cast<const float4*>(urow + j);
-                        a[j] = xmsub(a[j], lm, u.x);
-                        a[j + 1] = xmsub(a[j + 1], lm, u.y);
-                        a[j + 2] = xmsub(a[j + 2], lm, u.z);
-                        a[j + 3] = xmsub(a[j + 3], lm, u.w);
-                    }
+                for (int q = 0; q < N / 4; q++) {
+                    const float4 v = make_float4(4 * q >= k ? a[4 * q] : 0.0f, 4 * q + 1 >= k ? a[4 * q + 1] : 0.0f,
+                                                 4 * q + 2 >= k ? a[4 * q + 2] : 0.0f, 4 * q + 3 >= k ? a[4 * q + 3] : 0.0f);
+                    if (4 * q + 3 >= k) ur4[q] = v;
+                    __stcs(ug4 + q, v);
                 }
-                if constexpr (WPM == 1) __syncwarp();
+            }
+            gsync();
+            if constexpr (k < N - 1) {
+                const float4* ur4 = reinterpret_cast<const float4*>(urow);
+                const float piv = urow[k];
+                // rows that have already served as pivot rows are dead data: they divide the pivot by itself
+                // (a value on the fast division path) and are updated along with the live ones
+                const bool act = pos > k;
+                const float lm = xdiv(act ? a[k] : piv, make_divisor(piv));
+                if (act) sA[pos * N + k] = lm;
+                constexpr int q1 = (k + 1) / 4;  // the quad of column k+1 first: the next search only needs that column
+                {
+                    const float4 u = ur4[q1];
+                    if (4 * q1 > k) a[4 * q1] = xmsub(a[4 * q1], lm, u.x);
+                    if (4 * q1 + 1 > k) a[4 * q1 + 1] = xmsub(a[4 * q1 + 1], lm, u.y);
+                    if (4 * q1 + 2 > k) a[4 * q1 + 2] = xmsub(a[4 * q1 + 2], lm, u.z);
+                    a[4 * q1 + 3] = xmsub(a[4 * q1 + 3], lm, u.w);
+                }
+                cand = search(std::integral_constant<int, k + 1>{});
+#pragma unroll
+                for (int q = q1 + 1; q < N / 4; q++) {
+                    const float4 u = ur4[q];
+                    a[4 * q] = xmsub(a[4 * q], lm, u.x);
+                    a[4 * q + 1] = xmsub(a[4 * q + 1], lm, u.y);
+                    a[4 * q + 2] = xmsub(a[4 * q + 2], lm, u.z);
+                    a[4 * q + 3] = xmsub(a[4 * q + 3], lm, u.w);
+                }
             }
         });
         fence_async_smem();
@@ -619,17 +623,18 @@ static cudaError_t launch_lu_regs(const float* A, float* L, float* U, int* P, lo
 
 template <int N>
 static cudaError_t launch_lu_lane(const float* A, float* L, float* U, int* P, long batch, int pivoting, cudaStream_t st) {
-    constexpr size_t per_mat = (size_t)((N * N + 4) + 2 * N + (N * 9 + 3) / 4 * 4 + N + 8) * 4;
+    constexpr size_t per_mat = (size_t)((N * N + 4) + 2 * N + N + 8) * 4;
     constexpr int fit = (int)((227 * 1024 - 1024) / (per_mat + 8));
-    // registers bound the residency before shared memory does: a row of N floats per lane plus ~40 more
-    constexpr int by_regs = 65536 / ((N + 40) * N);
+    // registers bound the residency before shared memory does: a row of N floats per lane plus ~38 more
+    // (N = 64: 10 matrices per CTA; measured 9 / 10 / 12 matrices: 16.6 / 17.7 / 17.0 M fact/s)
+    constexpr int by_regs = 65536 / ((N + 38) * N);
     constexpr int MATS = fit * N > 1024 ? 1024 / N : (fit < by_regs ? fit : by_regs);
     const size_t smem = MATS * per_mat + MATS * sizeof(uint64_t);
-    auto kern = lu_lane_kernel<N, MATS>;
+    auto kern = pivoting ? lu_lane_kernel<N, MATS, true> : lu_lane_kernel<N, MATS, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     long grid = std::min<long>((batch + MATS - 1) / MATS, (long)sm_count());
-    kern<<<(unsigned)grid, MATS * N, smem, st>>>(A, L, U, P, batch, pivoting);
+    kern<<<(unsigned)grid, MATS * N, smem, st>>>(A, L, U, P, batch);
     count_launch();
     return cudaGetLastError();
 }
