@@ -662,7 +662,7 @@ cudaError_t lu_exact(const float* A, float* L, float* U, int* P, int n, long bat
         if (aligned && n == 4) return launch_lu_tpm<4>(A, L, U, P, batch, pivoting, st);
         if (aligned && n == 8) return launch_lu_regs<8, 2, 20>(A, L, U, P, batch, pivoting, st);
         if (aligned && n == 16) return launch_lu_regs<16, 4, 12, true>(A, L, U, P, batch, pivoting, st);  // U rows straight out: +10 %
-        if (aligned && n == 32) return launch_lu_regs<32, 16, 10>(A, L, U, P, batch, pivoting, st);
+        if (aligned && n == 32) return launch_lu_regs<32, 16, 10>(A, L, U, P, batch, pivoting, st);  // (lane kernel: 97 M vs 121 M fact/s)
         if (aligned && n == 64) return launch_lu_lane<64>(A, L, U, P, batch, pivoting, st);
         if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
     }
