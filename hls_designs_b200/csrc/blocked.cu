@@ -1486,8 +1486,8 @@ lu_swap_kernel(float* __restrict__ Wk, const int* __restrict__ P, int n, int o) 
 // of column c stay where they were computed and are not carried along by later exchanges
 // (lu_v1.1/model4x4/lu.cpp:55-63 exchanges columns >= id only).  Undo, per column c, the panel's exchanges
 // k' > c, last one first; exchanges of later panels never touch these columns.  The touched rows
-// (<= 256) x 128 columns are staged in shared memory.  grid: (batch), 256 threads
-__global__ void __launch_bounds__(256)
+// (<= 256) x 128 columns are staged in shared memory.  grid: (batch), kUnswapThreads threads
+__global__ void __launch_bounds__(1024)
 lu_unswap_panel_kernel(float* __restrict__ L, const int* __restrict__ P, int n, int o) {
     extern __shared__ __align__(16) float us_tile[];  // [2 * NB][NB + 1] floats, then n ints (slot map)
     __shared__ int piv[NB], pos[2 * NB], pslot[NB];
@@ -1495,13 +1495,13 @@ lu_unswap_panel_kernel(float* __restrict__ L, const int* __restrict__ P, int n, 
     constexpr int ld = NB + 1;
     int* slotmap = reinterpret_cast<int*>(us_tile + 2 * NB * ld);
     if (threadIdx.x < NB) piv[threadIdx.x] = P[(long)blockIdx.x * n + o + threadIdx.x];
-    for (int i = threadIdx.x; i < n; i += 256) slotmap[i] = -1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) slotmap[i] = -1;
     __syncthreads();
     if (threadIdx.x == 0) ntouch = lu_touched_rows(piv, o, pos, pslot, slotmap);
     __syncthreads();
     const int cnt = ntouch;
     float* base = L + (long)blockIdx.x * n * n + o;
-    for (int e = threadIdx.x; e < cnt * NB; e += 256) {
+    for (int e = threadIdx.x; e < cnt * NB; e += blockDim.x) {
         const int q = e >> 7, c = e & (NB - 1);
         us_tile[q * ld + c] = base[(long)pos[q] * n + c];
     }
@@ -1518,7 +1518,7 @@ lu_unswap_panel_kernel(float* __restrict__ L, const int* __restrict__ P, int n, 
         }
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < cnt * NB; e += 256) {
+    for (int e = threadIdx.x; e < cnt * NB; e += blockDim.x) {
         const int q = e >> 7, c = e & (NB - 1);
         base[(long)pos[q] * n + c] = us_tile[q * ld + c];
     }
@@ -1544,6 +1544,8 @@ lu_transpose_kernel(float* __restrict__ Wk, float* __restrict__ T, int n, int o)
         for (int r = ty; r < 32; r += 8) wk[(long)(k0 + r) * n + c0 + tx] = tile[tx][r];
     }
 }
+
+constexpr int kUnswapThreads = 1024;  // the gather / scatter of the touched rows is latency bound: more loads in flight
 
 cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long batch, cudaStream_t st) {
     if (n % NB != 0 || n < 2 * NB || n > 1024) return cudaErrorNotSupported;
@@ -1574,7 +1576,7 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
         lu_panel_kernel<<<nb, std::max(256, n - o), 0, st>>>(U, L, P, n, o);
         count_launch();
         if (mt == 0) {  // last panel: nothing to update, only its L columns go back to the reference's convention
-            lu_unswap_panel_kernel<<<nb, 256, unswap_smem, st>>>(L, P, n, o);
+            lu_unswap_panel_kernel<<<nb, kUnswapThreads, unswap_smem, st>>>(L, P, n, o);
             count_launch();
             break;
         }
@@ -1600,7 +1602,7 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
         h.tiles_col = mt;
         gemm_tile_kernel<1><<<dim3(mt * mt, nb), 256, MmaSmem::kTotal, st>>>(h);
         count_launch();
-        lu_unswap_panel_kernel<<<nb, 256, unswap_smem, st>>>(L, P, n, o);  // L21 has served as operand
+        lu_unswap_panel_kernel<<<nb, kUnswapThreads, unswap_smem, st>>>(L, P, n, o);  // L21 has served as operand
         count_launch();
     }
     e = cudaGetLastError();
