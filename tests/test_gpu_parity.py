@@ -155,6 +155,64 @@ def test_edge_cases():
         hd.qr(np.ones((3, 5), np.float32))
 
 
+def _special_batch(kind, n, rng):
+    """Matrices that leave the fast paths of the kernels' square root / division (zeros, signed zeros,
+    subnormals, huge and tiny magnitudes, infinities, NaNs) next to ordinary ones."""
+    batch = 64
+    A = gen_spd(n, batch=batch, seed=n) if kind == "chol" else gen_full_rank(n, n, batch=batch, seed=n)
+    eye = np.eye(n, dtype=np.float32)
+    A[0] = eye                                              # zeros everywhere off the diagonal
+    A[1] = np.diag(np.arange(1, n + 1, dtype=np.float32))
+    A[2] = 4 * eye + np.eye(n, k=1, dtype=np.float32) + np.eye(n, k=-1, dtype=np.float32)  # banded
+    i, j = rng.integers(0, n, 2 * n).reshape(2, n)
+    A[3][i, j] = 0.0
+    A[3][j, i] = 0.0
+    A[4] *= np.float32(1e-25)
+    A[5] *= np.float32(1e25)
+    A[6] *= np.float32(1e-37)                               # subnormal intermediates
+    A[7][i, j] = -0.0
+    A[8][n // 2, n // 3] = np.nan
+    A[9][n - 1, 0] = np.inf
+    A[10] = 0.0
+    A[11][:, 0] = 0.0                                       # zero pivot column
+    A[12] *= np.float32(2.0 ** 60)                          # the guard's upper bound
+    A[13] *= np.float32(2.0 ** -60)
+    A[14] = -A[14]
+    A[15][n - 1] = A[15][0]                                 # two equal rows: exact zeros appear during elimination
+    return A
+
+
+@pytest.mark.parametrize("kind", ("chol", "lu", "qr"))
+def test_special_values_bit_exact(kind):
+    """Zeros, signed zeros, subnormals, extreme magnitudes, infinities and NaNs through every fast kernel size:
+    NaNs where the csim has NaNs, every other bit identical (the shared-reciprocal division and the
+    'scratch lanes divide the pivot by itself' tricks of the kernels must not change any value)."""
+    rng = np.random.default_rng(77)
+    with np.errstate(all="ignore"):
+        for n in (4, 8, 16, 32, 64):
+            A = _special_batch(kind, n, rng)
+            if kind == "chol":
+                designs = ("cholesky_v1.3", "cholesky_v2.2")
+                run = lambda d: ([hd.cholesky(A, design=d)], [restate.cholesky(A, d, threads=8)])
+            elif kind == "lu":
+                designs = ("lu_v1.1", "nopivot")
+                run = lambda d: (hd.lu(A, design=d), restate.lu(A, pivoting=d != "nopivot", threads=8))
+            else:
+                designs = ("qr_v2.1", "qr_v1.1")
+                run = lambda d: (hd.qr(A, design=d), restate.qr(A, d, threads=8))
+            for d in designs:
+                got, want = run(d)
+                for g, w in zip(got, want):
+                    if g.dtype.kind == "f":
+                        gn, wn = np.isnan(g), np.isnan(w)
+                        bad = np.argwhere(gn != wn)
+                        assert bad.size == 0, f"{kind} n={n} {d}: NaN pattern differs first at {bad[0]}"
+                        ok = ~wn
+                        assert bits_equal(g[ok], w[ok]), f"{kind} n={n} {d}: {first_mismatch(np.where(ok, g, 0), np.where(ok, w, 0))}"
+                    else:
+                        assert np.array_equal(g, w), f"{kind} n={n} {d}: pivots differ"
+
+
 # ---------------------------------------------------------------- BASELINE.json full sizes, by property
 def test_full_size_cholesky_n16_batch_1m_properties():
     """configs[1]: batched Cholesky fp32 N=16, batch 1M.  Residual on the device for every matrix,
