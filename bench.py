@@ -395,6 +395,16 @@ def main():
             lib.hlsd_host_free(p)
 
     clocks = sampler.summary()
+    if roofline["bound"] == "hbm":
+        # context for the exact kernels that are not HBM-bound: the reference's arithmetic has no fused
+        # multiply-add (every float operation is rounded separately), so the arithmetic ceiling is one
+        # operation per FP32 lane and clock, not two
+        props = torch.cuda.get_device_properties(dev)
+        ghz = (clocks.get("sm_max_mhz") or 1965) / 1e3
+        peak = props.multi_processor_count * 128 * ghz / 1e3  # Tflop/s without FMA
+        roofline["fp32_unfused"] = {"achieved": gflops / 1e3, "peak": peak, "unit": "TFLOP/s", "frac": gflops / 1e3 / peak,
+                                    "note": "useful flops of the factorisation / (SMs x 128 FP32 lanes x max clock); "
+                                            "the exact kernels issue separately rounded multiplies and adds"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_rate(kind, rows, cols, design, args.cpu_seconds)
