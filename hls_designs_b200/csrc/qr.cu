@@ -509,9 +509,9 @@ qr_wave_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// Wavefront with Q in registers (qr_v2.1 arithmetic, square N = 64, 128): one CTA of 2N threads per matrix.
-// Threads 0..N-1 work on R in shared memory exactly like qr_factor (angle generation, columns right of c);
-// thread N + j keeps ROW j of Q - two thirds of all rotation work - in N registers.  A rotation of a step
+// Wavefront with Q in registers (qr_v2.1 arithmetic, square N = 64, 128): one CTA of RT + N threads per matrix.
+// Threads 0..RT-1 work on R in shared memory exactly like qr_factor (angle generation, columns right of c);
+// thread RT + j keeps ROW j of Q - two thirds of all rotation work - in N registers.  A rotation of a step
 // touches rows (hi-1, hi) with hi = N-1-step + 2c, so within one step all pairs have the same alignment:
 // pair slot p = rows (2p + par - 1, 2p + par), par = parity of N-1-step, and the active slots are the
 // contiguous range p0 + c_lo .. p0 + c_hi.  The slot loop is unrolled (register indices are constants),
@@ -519,8 +519,8 @@ qr_wave_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
 // offset from a per-step base pointer.  Per rotation and Q row: one 8-byte shared-memory load and the six
 // floating-point operations, instead of two loads, two stores and address arithmetic on top.
 // ------------------------------------------------------------------------------------------------
-template <int N>
-__global__ void __launch_bounds__(2 * N, N == 64 ? 4 : 1)
+template <int N, int RT>
+__global__ void __launch_bounds__(RT + N, N == 64 ? 4 : 1)
 qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restrict__ R, long batch) {
     extern __shared__ __align__(16) float smem_f[];
     constexpr int ldr = N | 1;
@@ -529,13 +529,13 @@ qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
     // unconditionally and discard); N * ldr is even, so the buffer is 8-byte aligned
     float2* cs2 = reinterpret_cast<float2*>(r + N * ldr) + 8;
     const int t = threadIdx.x;
-    const bool q_side = t >= N;
+    const bool q_side = t >= RT;  // threads 0..RT-1 work on R, thread RT + j holds row j of Q
     for (long b = blockIdx.x; b < batch; b += gridDim.x) {
         const float* a = A + b * (long)(N * N);
-        for (int e = t; e < N * N; e += 2 * N) r[(e / N) * ldr + (e % N)] = a[e];
+        for (int e = t; e < N * N; e += RT + N) r[(e / N) * ldr + (e % N)] = a[e];
         float qq[N];
 #pragma unroll
-        for (int i = 0; i < N; i++) qq[i] = (q_side && i == t - N) ? 1.0f : 0.0f;
+        for (int i = 0; i < N; i++) qq[i] = (q_side && i == t - RT) ? 1.0f : 0.0f;
         __syncthreads();
         constexpr int last_t = (N - 1) + 2 * (N - 1);
         for (int step = 0; step <= last_t; step++) {
@@ -545,7 +545,7 @@ qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
             if (nrot <= 0) continue;
             const int i0 = N - 1 - step + 2 * c_lo;  // row index of rotation k: i0 + 2 k
             if (!q_side) {
-                for (int k = t; k < nrot; k += N) {
+                for (int k = t; k < nrot; k += RT) {
                     const int c = c_lo + k, i = i0 + 2 * k;
                     float lo = r[(i - 1) * ldr + c], hi = r[i * ldr + c];
                     float cc, ss;
@@ -558,7 +558,7 @@ qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
             __syncthreads();
             if (!q_side) {
                 // R: columns x = tx, tx + 32, ... take the rotations with c < x; rotations k = ty, ty + GY, ...
-                constexpr int GY = N / 32;
+                constexpr int GY = RT / 32;
                 const int tx = t & 31, ty = t >> 5;
                 // sixteen (N = 128) independent rotations per turn and thread: four rotations on each of the thread's
                 // columns; all loads, then the arithmetic, then all stores (the rotations of a step touch disjoint
@@ -644,9 +644,9 @@ qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
             __syncthreads();
         }
         float* ro = R + b * (long)(N * N);
-        for (int e = t; e < N * N; e += 2 * N) ro[e] = r[(e / N) * ldr + (e % N)];
+        for (int e = t; e < N * N; e += RT + N) ro[e] = r[(e / N) * ldr + (e % N)];
         if (q_side) {
-            float4* q4 = reinterpret_cast<float4*>(Q + b * (long)(N * N) + (long)(t - N) * N);
+            float4* q4 = reinterpret_cast<float4*>(Q + b * (long)(N * N) + (long)(t - RT) * N);
 #pragma unroll
             for (int v = 0; v < N / 4; v++) q4[v] = make_float4(qq[4 * v], qq[4 * v + 1], qq[4 * v + 2], qq[4 * v + 3]);
         }
@@ -734,16 +734,16 @@ static int qr_regs_mode() {
     return mode;
 }
 
-template <int N>
+template <int N, int RT>
 static cudaError_t launch_qr_qreg(const float* A, float* Q, float* R, long batch, cudaStream_t st) {
-    const size_t smem = ((size_t)N * (N | 1) + 2 * (N / 2 + 2 + 8 + 16)) * 4;
-    auto kern = qr_qreg_kernel<N>;
+    const size_t smem = ((size_t)N * (N | 1) + 2 * (N / 2 + 2 + 8 + 4 * (RT / 32))) * 4;  // slack behind cs: 3 * GY entries
+    auto kern = qr_qreg_kernel<N, RT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 2 * N, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RT + N, smem);
     long grid = std::min<long>(batch, (long)sm_count() * std::max(1, per_sm));
-    kern<<<(unsigned)grid, 2 * N, smem, st>>>(A, Q, R, batch);
+    kern<<<(unsigned)grid, RT + N, smem, st>>>(A, Q, R, batch);
     count_launch();
     return cudaGetLastError();
 }
@@ -791,8 +791,10 @@ static cudaError_t qr_dispatch(const float* A, float* Q, float* R, int rows, int
         if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
     }
     if (VARIANT == 0 && aligned && rows == cols && path == HLSD_PATH_AUTO && qr_regs_mode() == 0) {
-        if (rows == 64) return launch_qr_qreg<64>(A, Q, R, batch, st);
-        if (rows == 128) return launch_qr_qreg<128>(A, Q, R, batch, st);
+        if (rows == 64) return launch_qr_qreg<64, 64>(A, Q, R, batch, st);
+        // (256 R threads would halve the R side of a step, but 384 threads cap the kernel at 168 registers and the
+        // 128-register Q rows spill: 217 k instead of 545 k fact/s)
+        if (rows == 128) return launch_qr_qreg<128, 128>(A, Q, R, batch, st);
     }
     const size_t per = qr_smem_per_matrix(rows, cols);
     const size_t cap = 227 * 1024 - 1024;
