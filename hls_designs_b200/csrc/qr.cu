@@ -791,7 +791,7 @@ static cudaError_t qr_dispatch(const float* A, float* Q, float* R, int rows, int
         if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
     }
     if (VARIANT == 0 && aligned && rows == cols && path == HLSD_PATH_AUTO && qr_regs_mode() == 0) {
-        if (rows == 64) return launch_qr_qreg<64, 64>(A, Q, R, batch, st);
+        if (rows == 64) return launch_qr_qreg<64, 64>(A, Q, R, batch, st);  // (128 R threads, 3 CTAs per SM: 4.0 M vs 5.2 M fact/s)
         // (256 R threads would halve the R side of a step, but 384 threads cap the kernel at 168 registers and the
         // 128-register Q rows spill: 217 k instead of 545 k fact/s)
         if (rows == 128) return launch_qr_qreg<128, 128>(A, Q, R, batch, st);
