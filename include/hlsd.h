@@ -64,10 +64,12 @@ typedef enum {
 
 /* flags: low byte selects the kernel family (0 = automatic by size). */
 #define HLSD_PATH_AUTO 0
-#define HLSD_PATH_TPM 1     /* thread-per-matrix, register resident (N in {4, 8, 16})        */
-#define HLSD_PATH_GROUP 2   /* warp/CTA per matrix, shared-memory resident                     */
-#define HLSD_PATH_GLOBAL 3  /* one CTA per matrix in global memory: any N, exact, slow         */
-#define HLSD_PATH_BLOCKED 4 /* blocked right-looking, fp32 SIMT trailing update (exact order)  */
+#define HLSD_PATH_TPM 1     /* the register-resident kernels (one thread or a few lanes per matrix):
+                               N in {4, 8, 16, 32, 64}, Cholesky also 128; exact                      */
+#define HLSD_PATH_GROUP 2   /* warp/CTA per matrix, shared-memory resident; exact                     */
+#define HLSD_PATH_GLOBAL 3  /* one CTA per matrix in global memory: any N, exact, slow                */
+#define HLSD_PATH_BLOCKED 4 /* reserved (blocked with an exact-order SIMT trailing update): not built,
+                               returns HLSD_ERR_UNSUPPORTED                                            */
 #define HLSD_PATH_TENSOR 5  /* blocked right-looking, tcgen05 tensor-core trailing update:
                                Cholesky n >= 256, n % 128 == 0; LU 256 <= n <= 1024, n % 128 == 0     */
 #define HLSD_PATH_MASK 0xff
