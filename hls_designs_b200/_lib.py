@@ -19,6 +19,9 @@ SIGNATURES = {
     "hlsd_cholesky_dev": (_i, [_vp, _vp, _i, _i64, _i, _i, _vp]),
     "hlsd_lu_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp]),
     "hlsd_qr_dev": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i, _i, _vp]),
+    "hlsd_cholesky_host_multi": (_i, [_vp, _vp, _i, _i64, _i, _i, _vp, _i]),
+    "hlsd_lu_host_multi": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp, _i]),
+    "hlsd_qr_host_multi": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i, _i, _vp, _i]),
     "hlsd_host_alloc": (_vp, [ctypes.c_size_t]),
     "hlsd_host_free": (None, [_vp]),
     "hlsd_release_workspace": (None, []),
@@ -28,6 +31,7 @@ SIGNATURES = {
     "hlsd_last_error": (ctypes.c_char_p, []),
     "hlsd_version": (ctypes.c_char_p, []),
     "hlsd_selftest_division": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "hlsd_selftest_copy_host": (_i, [_vp, _vp, ctypes.c_size_t, ctypes.c_size_t, _i64]),
 }
 
 _lib = None

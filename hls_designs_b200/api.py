@@ -5,9 +5,14 @@
     Q, R    = qr(A)                  <->  top(A, Q, R)     QR/*/model4x4/qr.h:22-24
 
 `A` is either a numpy array on the host (goes through the hlsd_*_host C entry points: copy in,
-factor on the GPU, copy out) or a torch CUDA tensor (hlsd_*_dev on torch's current stream, outputs
+factor on the GPU, copy out; with `devices=[...]` through hlsd_*_host_multi, which splits the
+batch over several GPUs) or a torch CUDA tensor (hlsd_*_dev on torch's current stream, outputs
 are torch tensors on the same device).  Shapes: (..., n, n) / (..., rows, cols); leading
 dimensions are flattened into the batch.  Everything is float32, row-major, as in the reference.
+
+`exact=True` (HLSD_FLAG_EXACT) keeps the reference design's arithmetic at every size (no tensor
+path); `fused=True` (HLSD_FLAG_FUSED) lets the register-resident kernels contract multiply-subtract
+pairs into FMAs (not bit-identical; see include/hlsd.h).
 """
 import ctypes
 
@@ -19,6 +24,7 @@ CHOL_DESIGNS = {"cholesky_v1.3": 13, "cholesky_v2.2": 22, "cholesky_v3.2": 32, "
 LU_DESIGNS = {"lu_v1.1": 11, "lu_v1.2": 12, "lu_v2.1": 21, "nopivot": 1}
 QR_DESIGNS = {"qr_v1.1": 11, "qr_v1.2": 12, "qr_v2.1": 21}
 PATHS = {"auto": 0, "tpm": 1, "group": 2, "global": 3, "blocked": 4, "tensor": 5}
+FLAG_EXACT, FLAG_FUSED = 0x100, 0x200
 
 
 def _is_torch(x):
@@ -31,10 +37,20 @@ def _design(table, design):
     return table[design]
 
 
-def _path(path):
+def _path(path, exact=False, fused=False):
     if path not in PATHS:
         raise ValueError(f"unknown path {path!r}; one of {sorted(PATHS)}")
-    return PATHS[path]
+    return PATHS[path] | (FLAG_EXACT if exact else 0) | (FLAG_FUSED if fused else 0)
+
+
+def _devices(devices):
+    """-> (ctypes int array or None, count) for the *_host_multi entry points."""
+    if devices is None:
+        return None, 0
+    if isinstance(devices, int):  # the first `devices` GPUs
+        return None, int(devices)
+    arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+    return arr, len(devices)
 
 
 def _np_in(A, square):
@@ -67,8 +83,8 @@ def _stream(t):
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
-def cholesky(A, design="cholesky_v1.3", path="auto"):
-    lib, d, p = _lib.load(), _design(CHOL_DESIGNS, design), _path(path)
+def cholesky(A, design="cholesky_v1.3", path="auto", exact=False, fused=False, devices=None):
+    lib, d, p = _lib.load(), _design(CHOL_DESIGNS, design), _path(path, exact, fused)
     if _is_torch(A):
         import torch
         A, batch = _torch_in(A, True)
@@ -78,12 +94,16 @@ def cholesky(A, design="cholesky_v1.3", path="auto"):
         return L
     A, batch = _np_in(A, True)
     L = np.empty_like(A)
-    _lib.check(lib.hlsd_cholesky_host(A.ctypes.data, L.ctypes.data, A.shape[-1], batch, d, p))
+    if devices is not None:
+        devs, nd = _devices(devices)
+        _lib.check(lib.hlsd_cholesky_host_multi(A.ctypes.data, L.ctypes.data, A.shape[-1], batch, d, p, devs, nd))
+    else:
+        _lib.check(lib.hlsd_cholesky_host(A.ctypes.data, L.ctypes.data, A.shape[-1], batch, d, p))
     return L
 
 
-def lu(A, design="lu_v1.1", path="auto"):
-    lib, d, p = _lib.load(), _design(LU_DESIGNS, design), _path(path)
+def lu(A, design="lu_v1.1", path="auto", exact=False, fused=False, devices=None):
+    lib, d, p = _lib.load(), _design(LU_DESIGNS, design), _path(path, exact, fused)
     if _is_torch(A):
         import torch
         A, batch = _torch_in(A, True)
@@ -96,12 +116,17 @@ def lu(A, design="lu_v1.1", path="auto"):
     A, batch = _np_in(A, True)
     L, U = np.empty_like(A), np.empty_like(A)
     P = np.empty(A.shape[:-1], dtype=np.int32)
-    _lib.check(lib.hlsd_lu_host(A.ctypes.data, L.ctypes.data, U.ctypes.data, P.ctypes.data, A.shape[-1], batch, d, p))
+    if devices is not None:
+        devs, nd = _devices(devices)
+        _lib.check(lib.hlsd_lu_host_multi(A.ctypes.data, L.ctypes.data, U.ctypes.data, P.ctypes.data, A.shape[-1], batch, d, p,
+                                          devs, nd))
+    else:
+        _lib.check(lib.hlsd_lu_host(A.ctypes.data, L.ctypes.data, U.ctypes.data, P.ctypes.data, A.shape[-1], batch, d, p))
     return L, U, P
 
 
-def qr(A, design="qr_v2.1", path="auto"):
-    lib, d, p = _lib.load(), _design(QR_DESIGNS, design), _path(path)
+def qr(A, design="qr_v2.1", path="auto", exact=False, fused=False, devices=None):
+    lib, d, p = _lib.load(), _design(QR_DESIGNS, design), _path(path, exact, fused)
     if _is_torch(A):
         import torch
         A, batch = _torch_in(A, False)
@@ -115,7 +140,11 @@ def qr(A, design="qr_v2.1", path="auto"):
     rows, cols = A.shape[-2:]
     Q = np.empty(A.shape[:-2] + (rows, rows), dtype=np.float32)
     R = np.empty_like(A)
-    _lib.check(lib.hlsd_qr_host(A.ctypes.data, Q.ctypes.data, R.ctypes.data, rows, cols, batch, d, p))
+    if devices is not None:
+        devs, nd = _devices(devices)
+        _lib.check(lib.hlsd_qr_host_multi(A.ctypes.data, Q.ctypes.data, R.ctypes.data, rows, cols, batch, d, p, devs, nd))
+    else:
+        _lib.check(lib.hlsd_qr_host(A.ctypes.data, Q.ctypes.data, R.ctypes.data, rows, cols, batch, d, p))
     return Q, R
 
 
@@ -124,13 +153,13 @@ def launch_count():
 
 
 def selftest_division(num, den):
-    """(mismatches, fast_pairs) of the kernels' shared-divisor division against IEEE division over two
-    equally long float32 CUDA tensors (diagnostic; see include/hlsd.h)."""
+    """(mismatches, fast_pairs, unguarded_mismatches) of the kernels' shared-divisor division against IEEE
+    division over two equally long float32 CUDA tensors (diagnostic; see include/hlsd.h)."""
     import torch
     assert num.is_cuda and den.is_cuda and num.dtype == den.dtype == torch.float32 and num.numel() == den.numel()
     num, den = num.contiguous(), den.contiguous()
-    out = torch.zeros(2, dtype=torch.int64, device=num.device)
+    out = torch.zeros(3, dtype=torch.int64, device=num.device)
     with torch.cuda.device(num.device):
         _lib.check(_lib.load().hlsd_selftest_division(num.data_ptr(), den.data_ptr(), num.numel(), out.data_ptr(), _stream(num)))
-    bad, fast = out.tolist()
-    return bad, fast
+    bad, fast, unguarded = out.tolist()
+    return bad, fast, unguarded

@@ -55,25 +55,27 @@ def build(force=False, verbose=False):
     return LIB
 
 
-HOST = os.path.join(HERE, "host")
-HOST_BIN = os.path.join(HOST, "bin")
+HOST = os.path.join(HERE, "host")                       # the drop-in top() headers (product)
+TB_DIR = os.path.join(HERE, "..", "tests", "host")      # the testbench that exercises them (test code)
+HOST_BIN = os.path.join(TB_DIR, "bin")
 # (name, macros): host-side testbenches in the shape of the reference's *_tb.cpp, linked to libhlsd.so
-HOST_TBS = [("chol_tb_4", ["-DTB_CHOL", "-Dmatrix_size=4"]), ("chol_tb_16", ["-DTB_CHOL", "-Dmatrix_size=16"]),
+HOST_TBS = [("chol_tb_256", ["-DTB_CHOL", "-Dmatrix_size=256"]), ("lu_tb_256", ["-DTB_LU", "-Dmatrix_size=256"]),
+            ("chol_tb_4", ["-DTB_CHOL", "-Dmatrix_size=4"]), ("chol_tb_16", ["-DTB_CHOL", "-Dmatrix_size=16"]),
             ("chol_tb_64", ["-DTB_CHOL", "-Dmatrix_size=64"]),
             ("lu_tb_16", ["-DTB_LU", "-Dmatrix_size=16"]), ("lu_tb_64", ["-DTB_LU", "-Dmatrix_size=64"]),
             ("qr_tb_16x16", ["-DTB_QR", "-DROWS=16", "-DCOLS=16"]), ("qr_tb_64x64", ["-DTB_QR", "-DROWS=64", "-DCOLS=64"])]
 
 
 def host_testbenches():
-    """g++ builds of host/tb.cpp against the drop-in headers (C++ host side above the C ABI)."""
+    """g++ builds of tests/host/tb.cpp against the drop-in headers (C++ host side above the C ABI)."""
     os.makedirs(HOST_BIN, exist_ok=True)
-    src = os.path.join(HOST, "tb.cpp")
+    src = os.path.join(TB_DIR, "tb.cpp")
     for name, macros in HOST_TBS:
         out = os.path.join(HOST_BIN, name)
         if os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(LIB)):
             continue
         cmd = ["g++", "-O2", "-std=c++14", "-ffp-contract=off"] + macros + ["-I" + HOST, "-I" + os.path.join(HERE, "..", "include"),
-               src, "-o", out, "-L" + HERE, "-lhlsd", "-Wl,-rpath,$ORIGIN/../.."]
+               src, "-o", out, "-L" + HERE, "-lhlsd", "-Wl,-rpath,$ORIGIN/../../../hls_designs_b200"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("host testbench build failed:\n" + res.stderr)

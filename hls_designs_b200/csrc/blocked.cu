@@ -7,11 +7,13 @@
 // below the diagonal block).  That part runs on the tcgen05 tensor cores; everything that is not a
 // dense contraction stays on CUDA cores:
 //
-//   per panel p (columns o = 128 p .. o+127), all matrices of the batch at once (panel 0 reads its
-//   inputs straight from A, so the operand is never copied):
-//     1. blk_diag_kernel   (SIMT, register-tiled)          L11 = chol(A11), W = inv(L11)
-//     2. blk_mma_kernel<TRSM>  (tcgen05)  L21 = A21 * W^T        (rows below the diagonal block)
-//     3. blk_mma_kernel<SYRK>  (tcgen05)  A22 -= L21 * L21^T     (lower block triangle only)
+//   per block column q (columns o = 128 q .. o+127), all matrices of the batch at once (block column 0 reads
+//   its inputs straight from A, so the operand is never copied), LEFT-looking:
+//     1. blk_ll2_kernel  (tcgen05)  X[r][q] = A[r][q] - sum_{j<q} L[r][j] L[q][j]^T   (all earlier panels at once)
+//     2. blk_diag_kernel (SIMT, register-tiled)   L11 = chol(X[q][q]), W = inv(L11)
+//     3. blk_mma_kernel  (tcgen05)  L[r][q] = X[r][q] * W^T                            (rows below the diagonal block)
+//   (A right-looking variant - one SYRK launch per panel - and two one-tile-per-CTA update kernels were measured in
+//   round 1 and removed in round 2: 20 % / 8 % slower)
 //
 // Tensor-core arithmetic: fp32 operands are split on the fly into tf32 hi (truncation) + tf32 lo parts and each
 // product is formed as a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (3xTF32) with fp32 accumulation in TMEM,
@@ -19,7 +21,7 @@
 // the csim (different summation order, split products) but agrees to fp32 round-off level; the
 // exact paths (HLSD_PATH_GLOBAL) remain available at any N.
 //
-// blk_mma_kernel: one CTA = one 128x128 output tile, D = A * B^T with A = 128 rows x 128 k,
+// blk_mma_kernel / gemm_tile_kernel: one CTA = one 128x128 output tile, D = A * B^T with A = 128 rows x 128 k,
 // B = 128 rows x 128 k, both K-major fp32 in global memory.  K is consumed in four chunks of 32:
 // cp.async (LDGSTS) copies the raw fp32 chunk of A and B straight into shared memory in the
 // canonical K-major SWIZZLE_128B layout, double-buffered so that chunk c+1 streams in while chunk
@@ -28,8 +30,7 @@
 // 96 KB per CTA, two CTAs per SM overlap each other's MMA and epilogue phases; one elected
 // thread issues 12 tcgen05.mma.kind::tf32 (M128 N128 K8) per chunk; completion is tracked with
 // tcgen05.commit on an mbarrier; the epilogue reads the accumulator with tcgen05.ld (32x32b.x32)
-// and either stores it (TRSM) or subtracts it from C in place (SYRK).
-#include <cstdlib>
+// and either stores it (TRSM) or subtracts it from C (blocked LU).
 
 #include "common.cuh"
 #include "kernels.h"
@@ -151,7 +152,7 @@ blk_zero_upper_kernel(float* __restrict__ L, int n) {
 // arithmetic (IEEE sqrt and division, separately rounded multiply and subtract, per-element update order
 // k ascending as in cholesky_v1.3/model4x4/chol.cpp:25-63): the bit-identical 128 x 128 kernel.
 enum { DIAG_CHOL_INV = 0, DIAG_INV_ONLY = 1, DIAG_EXACT = 2 };
-template <int MODE>
+template <int MODE, bool FUSED = false>  // FUSED (with DIAG_EXACT): the contraction HLSD_FLAG_FUSED allows
 __global__ void __launch_bounds__(512, 2)
 blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __restrict__ W, int n, int o) {
     constexpr bool INV_ONLY = MODE == DIAG_INV_ONLY;
@@ -234,7 +235,7 @@ blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __res
 #pragma unroll
                 for (int b = EXACT ? BK : 0; b <= 2 * AK + 1; b++) {
                     if constexpr (EXACT) {
-                        if (i > k) v[AK][b] = xmsub(v[AK][b], lr, u[b]);  // rows <= k are not touched (0 * inf would be NaN)
+                        if (i > k) v[AK][b] = msub<FUSED>(v[AK][b], lr, u[b]);  // rows <= k are not touched (0 * inf would be NaN)
                     } else {
                         v[AK][b] = fmaf(-lr, u[b], v[AK][b]);
                     }
@@ -246,7 +247,7 @@ blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __res
                 // columns j = w + 16 b > i are never needed: i <= 32 a + 31, so b <= 2 a + 1 suffices
 #pragma unroll
                 for (int b = EXACT ? BK : 0; b <= 2 * a + 1; b++)
-                    v[a][b] = EXACT ? xmsub(v[a][b], lr, u[b]) : fmaf(-lr, u[b], v[a][b]);
+                    v[a][b] = EXACT ? msub<FUSED>(v[a][b], lr, u[b]) : fmaf(-lr, u[b], v[a][b]);
             });
         }
     });
@@ -274,8 +275,6 @@ blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __res
 // ------------------------------------------------------------------------------------------------
 // tensor-core tile kernel
 // ------------------------------------------------------------------------------------------------
-enum { MMA_TRSM = 0, MMA_SYRK = 1 };
-
 struct MmaSmem {
     // per 32-wide K chunk an operand tile is 128 rows x 32 k fp32 = one swizzle atom [128 rows][128 B].
     // raw fp32 tiles (2 stages x {A, B}) are filled by cp.async and double as the tf32 "hi" operands:
@@ -310,9 +309,7 @@ __device__ __forceinline__ float4 lo_of(float4 v) {
     return l;
 }
 
-// grid: (tiles, batch).  TRSM: tile t = row block t of the panel below the diagonal block.
-//                         SYRK: tile t -> (tj >= ti) in the lower block triangle of the trailing matrix.
-template <int MODE>
+// TRSM tiles of the blocked Cholesky: L[r][q] = X[r][q] * W^T.  grid: (row blocks below the diagonal block, batch)
 __global__ void __launch_bounds__(256, MmaSmem::kStages == 1 ? 3 : 2)
 blk_mma_kernel(const float* __restrict__ S, float* __restrict__ L, const float* __restrict__ W, int n, int o) {
     extern __shared__ unsigned char smem_raw[];
@@ -323,34 +320,13 @@ blk_mma_kernel(const float* __restrict__ S, float* __restrict__ L, const float* 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     float* Lb = L + (long)blockIdx.y * n * n;
     const float* Sb = S + (long)blockIdx.y * n * n;  // S = A for panel 0 (inputs not yet in L), L afterwards
-
-    int tj, ti;
-    if constexpr (MODE == MMA_TRSM) {
-        tj = blockIdx.x;
-        ti = 0;
-    } else {
-        // unrank blockIdx.x into (tj, ti), ti <= tj
-        int r = blockIdx.x;
-        tj = (int)((sqrtf(8.0f * r + 1.0f) - 1.0f) * 0.5f);
-        while ((tj + 1) * (tj + 2) / 2 <= r) tj++;
-        while (tj * (tj + 1) / 2 > r) tj--;
-        ti = r - tj * (tj + 1) / 2;
-    }
-    const int row0 = o + NB;  // first row of the panel below the diagonal block / of the trailing matrix
-    // operand rows (K-major, k = panel columns o .. o+127)
-    // TRSM multiplies the not yet factored panel rows (from S); SYRK multiplies finished L21 rows (from L)
-    const float* Arows = (MODE == MMA_TRSM ? Sb : Lb) + (long)(row0 + tj * NB) * n + o;
+    const int tj = blockIdx.x;
+    const int row0 = o + NB;  // first row of the panel below the diagonal block
+    // operand rows (K-major, k = panel columns o .. o+127): the not yet scaled panel rows X, and W (B[i][k] = W[i][k])
+    const float* Arows = Sb + (long)(row0 + tj * NB) * n + o;
     const long lda = n;
-    const float* Brows;
-    long ldb;
-    if constexpr (MODE == MMA_TRSM) {
-        Brows = W + (long)blockIdx.y * NB * NB;  // B[i][k] = W[i][k]  ->  D = A21 * W^T
-        ldb = NB;
-    } else {
-        Brows = Lb + (long)(row0 + ti * NB) * n + o;
-        ldb = n;
-    }
-    const bool same = (MODE == MMA_SYRK) && (tj == ti);
+    const float* Brows = W + (long)blockIdx.y * NB * NB;
+    const long ldb = NB;
 
     if (warp == 0) tmem_alloc(tmem_ptr, 128);
     if (t == 0) {
@@ -375,16 +351,16 @@ blk_mma_kernel(const float* __restrict__ S, float* __restrict__ L, const float* 
         for (int it = 0; it < 4; it++) {
             const int idx = it * 256 + t, row = idx >> 3, c4 = idx & 7;
             cp_async16(ra + piece_off(it), Arows + row * lda + chunk * MmaSmem::kChunkK + c4 * 4);
-            if (!same) cp_async16(rb + piece_off(it), Brows + row * ldb + chunk * MmaSmem::kChunkK + c4 * 4);
+            cp_async16(rb + piece_off(it), Brows + row * ldb + chunk * MmaSmem::kChunkK + c4 * 4);
         }
         cp_async_commit();
     };
     issue_loads(0);
     for (int chunk = 0; chunk < kChunks; chunk++) {
         unsigned char* ra = smem + MmaSmem::kRawA + (chunk % MmaSmem::kStages) * MmaSmem::kTileBytes;
-        unsigned char* rb = same ? ra : smem + MmaSmem::kRawB + (chunk % MmaSmem::kStages) * MmaSmem::kTileBytes;
+        unsigned char* rb = smem + MmaSmem::kRawB + (chunk % MmaSmem::kStages) * MmaSmem::kTileBytes;
         unsigned char* la = smem + MmaSmem::kLoA;
-        unsigned char* lb = same ? la : smem + MmaSmem::kLoB;
+        unsigned char* lb = smem + MmaSmem::kLoB;
         // the other raw stage was last read by the MMAs of chunk-1, which have completed (mbar_wait below)
         if (MmaSmem::kStages == 2 && chunk + 1 < kChunks) {
             issue_loads(chunk + 1);
@@ -397,7 +373,7 @@ blk_mma_kernel(const float* __restrict__ S, float* __restrict__ L, const float* 
         for (int it = 0; it < 4; it++) {
             const int off = piece_off(it);
             *reinterpret_cast<float4*>(la + off) = lo_of(*reinterpret_cast<const float4*>(ra + off));
-            if (!same) *reinterpret_cast<float4*>(lb + off) = lo_of(*reinterpret_cast<const float4*>(rb + off));
+            *reinterpret_cast<float4*>(lb + off) = lo_of(*reinterpret_cast<const float4*>(rb + off));
         }
         fence_async_smem();  // cp.async / st.shared data -> visible to the tensor core's async-proxy reads
         tc_fence_before();
@@ -425,7 +401,7 @@ blk_mma_kernel(const float* __restrict__ S, float* __restrict__ L, const float* 
     // epilogue.  TMEM -> registers (thread = accumulator row 32*(warp%4)+lane, 64 columns (warp/4)) ->
     // shared memory (the operand tiles are free now; 128 x 128 fp32 = 64 KB, 16-byte pieces XOR-swizzled
     // by row so that both the row-per-lane writes and the row-per-warp reads are conflict-free) ->
-    // coalesced read-modify-write of C, one 512-byte row per warp instruction.
+    // coalesced stores, one 512-byte row per warp instruction.
     {
         float* stage = reinterpret_cast<float*>(smem);
         const int drow = (warp & 3) * 32 + lane;
@@ -443,23 +419,12 @@ blk_mma_kernel(const float* __restrict__ S, float* __restrict__ L, const float* 
             }
         }
         __syncthreads();
-        float* Cbase;
-        if constexpr (MODE == MMA_TRSM) Cbase = Lb + (long)(row0 + tj * NB) * n + o;       // L21
-        else Cbase = Lb + (long)(row0 + tj * NB) * n + (row0 + ti * NB);                   // C tile
-        const float* Csrc = Sb + (long)(row0 + tj * NB) * n + (row0 + ti * NB);            // SYRK reads C from S
+        float* Cbase = Lb + (long)(row0 + tj * NB) * n + o;  // L21
 #pragma unroll 4
         for (int rr = 0; rr < 16; rr++) {
             const int row = warp * 16 + rr;
             const float4 d = *reinterpret_cast<const float4*>(stage + row * 128 + ((lane ^ (row & 7)) << 2));
-            float4* cp = reinterpret_cast<float4*>(Cbase + (long)row * n) + lane;
-            float4 v;
-            if constexpr (MODE == MMA_TRSM) {
-                v = d;
-            } else {
-                v = *(reinterpret_cast<const float4*>(Csrc + (long)row * n) + lane);
-                v.x -= d.x, v.y -= d.y, v.z -= d.z, v.w -= d.w;
-            }
-            *cp = v;
+            *(reinterpret_cast<float4*>(Cbase + (long)row * n) + lane) = d;
         }
     }
     tc_fence_before();
@@ -474,159 +439,11 @@ blk_mma_kernel(const float* __restrict__ S, float* __restrict__ L, const float* 
 // long enough to pipeline: global loads run two chunks ahead in registers, the threads write the raw
 // (= hi) and lo tiles of chunk c while the tensor core still multiplies chunk c-1 (both double
 // buffered), completion of chunk c-2 (tcgen05.commit -> one of two mbarriers) frees its buffers.
-// 128 KB of shared memory, one CTA per SM.  grid: (panels - q, batch): r = q + blockIdx.x
-// ------------------------------------------------------------------------------------------------
-struct LlSmem {
-    static constexpr int kTile = 128 * 32 * 4;                 // one operand chunk: 128 rows x 32 k
-    static constexpr int kRaw = 0;                             // [2][A, B] raw fp32 = tf32 hi operands
-    static constexpr int kLo = 4 * kTile;                      // [2][A, B] lo operands
-    static constexpr int kBar = 8 * kTile;                     // two mbarriers
-    static constexpr int kTmemPtr = kBar + 16;
-    static constexpr int kTotal = kBar + 32 + 1024;
-};
-
-constexpr int kLlThreads = 512;  // 16 warps: two 16-byte pieces per operand, chunk and thread
-
-__global__ void __launch_bounds__(kLlThreads, 1)
-blk_ll_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) {
-    extern __shared__ unsigned char smem_raw[];
-    // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the address space: LDS/STS, not generic LD/ST)
-    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LlSmem::kBar);
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + LlSmem::kTmemPtr);
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int r = q + blockIdx.x;
-    float* Lb = L + (long)blockIdx.y * n * n;
-    const float* Sb = S + (long)blockIdx.y * n * n;
-    const float* Arows = Lb + (long)r * NB * n;  // finished panels 0 .. q-1 of block row r
-    const float* Brows = Lb + (long)q * NB * n;  // ... and of block row q
-    const bool same = (r == q);
-    const int C = 4 * q;  // 32-wide K chunks
-
-    if (warp == 0) tmem_alloc(tmem_ptr, 128);
-    if (t == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        fence_mbar_init();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_d = *tmem_ptr;
-
-    constexpr int kPieces = 1024 / kLlThreads;  // 16-byte pieces per operand, chunk and thread
-    auto piece_off = [&](int it) {
-        const int idx = it * kLlThreads + t, row = idx >> 3, c4 = idx & 7;
-        return row * 128 + ((c4 ^ (row & 7)) << 4);
-    };
-    // Register-staged operand stream: chunk c+2 is loaded (plain 16-byte global loads) into the register
-    // buffer that chunk c has just vacated; at its turn a chunk is written to shared memory twice, as the
-    // raw tile (= tf32 hi operand) and as the lo tile.  (A cp.async ring would cost a third pass over
-    // shared memory - write raw, read raw, write lo - and shared-memory bandwidth is what bounds this
-    // kernel: the 12 MMAs of a chunk alone read 96 KB of operands from it.)
-    float4 bufA[2][kPieces], bufB[2][kPieces];
-    auto gload = [&](int c, float4 (&ba)[kPieces], float4 (&bb)[kPieces]) {
-        if (c < C) {
-#pragma unroll
-            for (int it = 0; it < kPieces; it++) {
-                const int idx = it * kLlThreads + t, row = idx >> 3, c4 = idx & 7;
-                ba[it] = __ldg(reinterpret_cast<const float4*>(Arows + (long)row * n + c * 32 + c4 * 4));
-                if (!same) bb[it] = __ldg(reinterpret_cast<const float4*>(Brows + (long)row * n + c * 32 + c4 * 4));
-            }
-        }
-    };
-    auto step = [&](int c, float4 (&ba)[kPieces], float4 (&bb)[kPieces]) {
-        if (c >= 2) {  // MMAs of chunk c-2 are done: raw and lo buffers of this parity are free
-            mbar_wait(&bars[c & 1], (uint32_t)(((c - 2) >> 1) & 1));
-            tc_fence_after();
-        }
-        unsigned char* ra = smem + LlSmem::kRaw + (c & 1) * 2 * LlSmem::kTile;
-        unsigned char* rb = same ? ra : ra + LlSmem::kTile;
-        unsigned char* la = smem + LlSmem::kLo + (c & 1) * 2 * LlSmem::kTile;
-        unsigned char* lb = same ? la : la + LlSmem::kTile;
-#pragma unroll
-        for (int it = 0; it < kPieces; it++) {
-            const int off = piece_off(it);
-            *reinterpret_cast<float4*>(ra + off) = ba[it];
-            *reinterpret_cast<float4*>(la + off) = lo_of(ba[it]);
-            if (!same) {
-                *reinterpret_cast<float4*>(rb + off) = bb[it];
-                *reinterpret_cast<float4*>(lb + off) = lo_of(bb[it]);
-            }
-        }
-        gload(c + 2, ba, bb);
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (t == 0) {
-            const uint64_t dAhi = make_sw128_desc(smem_u32(ra)), dAlo = make_sw128_desc(smem_u32(la));
-            const uint64_t dBhi = make_sw128_desc(smem_u32(rb)), dBlo = make_sw128_desc(smem_u32(lb));
-#pragma unroll
-            for (int kk = 0; kk < 4; kk++) {
-                const uint64_t adv = (uint64_t)((kk * 32) >> 4);
-                const uint32_t first = (c == 0 && kk == 0) ? 0u : 1u;
-                umma_tf32(tmem_d, dAlo + adv, dBhi + adv, kIdescTf32, first);
-                umma_tf32(tmem_d, dAhi + adv, dBlo + adv, kIdescTf32, 1u);
-                umma_tf32(tmem_d, dAhi + adv, dBhi + adv, kIdescTf32, 1u);
-            }
-            umma_commit(&bars[c & 1]);
-        }
-    };
-    gload(0, bufA[0], bufB[0]);
-    gload(1, bufA[1], bufB[1]);
-    for (int c = 0; c < C; c += 2) {  // C = 4 q is even
-        step(c, bufA[0], bufB[0]);
-        step(c + 1, bufA[1], bufB[1]);
-    }
-    // the C tile (from A) is fetched while the last chunks are still being multiplied
-    const long coff = (long)r * NB * n + (long)q * NB;
-    constexpr int kRowsPerWarp = 128 / (kLlThreads / 32);
-    float4 cv[kRowsPerWarp];
-#pragma unroll
-    for (int rr = 0; rr < kRowsPerWarp; rr++)
-        cv[rr] = *(reinterpret_cast<const float4*>(Sb + coff + (long)(warp * kRowsPerWarp + rr) * n) + lane);
-    // drain the last two chunks
-    mbar_wait(&bars[(C - 2) & 1], (uint32_t)(((C - 2) >> 1) & 1));
-    mbar_wait(&bars[(C - 1) & 1], (uint32_t)(((C - 1) >> 1) & 1));
-    tc_fence_after();
-    {
-        float* stage = reinterpret_cast<float*>(smem);
-        const int drow = (warp & 3) * 32 + lane;  // accumulator row = TMEM lane (warp % 4 selects the lane quarter)
-        constexpr int kColsPerWarp = 128 / (kLlThreads / 128);
-        const int dcol0 = (warp >> 2) * kColsPerWarp;
-#pragma unroll
-        for (int h = 0; h < kColsPerWarp / 32; h++) {
-            float acc[32];
-            const int col = dcol0 + h * 32;
-            tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col, acc);
-#pragma unroll
-            for (int qq = 0; qq < 8; qq++) {
-                const int c4 = (col >> 2) + qq;
-                *reinterpret_cast<float4*>(stage + drow * 128 + ((c4 ^ (drow & 7)) << 2)) =
-                    make_float4(acc[4 * qq], acc[4 * qq + 1], acc[4 * qq + 2], acc[4 * qq + 3]);
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int rr = 0; rr < kRowsPerWarp; rr++) {
-            const int row = warp * kRowsPerWarp + rr;
-            const float4 d = *reinterpret_cast<const float4*>(stage + row * 128 + ((lane ^ (row & 7)) << 2));
-            float4 v = cv[rr];
-            v.x -= d.x, v.y -= d.y, v.z -= d.z, v.w -= d.w;
-            *(reinterpret_cast<float4*>(Lb + coff + (long)row * n) + lane) = v;
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_d, 128);
-}
-
-// ------------------------------------------------------------------------------------------------
+// (A cp.async ring would cost a third pass over shared memory - write raw, read raw, write lo.)
 // Two row blocks per CTA: tiles (r0, q) and (r0 + 1, q) share the B operand (block row q), which cuts
-// the panel bytes each step re-reads from L2/HBM by a quarter - the measured bound of the update.
-// Same pipeline as blk_ll_kernel with three operand tiles per chunk (A0, A1, B: raw + lo, double
-// buffered = 192 KB) and two accumulators in TMEM (256 columns).  grid: (ceil((panels - q) / 2), batch)
+// the panel bytes each step re-reads from L2/HBM by a quarter - the measured bound of the update:
+// three operand tiles per chunk (A0, A1, B: raw + lo, double buffered = 192 KB) and two accumulators
+// in TMEM (256 columns).  grid: (ceil((panels - q) / 2), batch)
 // ------------------------------------------------------------------------------------------------
 struct Ll2Smem {
     static constexpr int kTile = 128 * 32 * 4;
@@ -787,228 +604,12 @@ blk_ll2_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q)
     if (warp == 0) tmem_dealloc(tmem_d, 256);
 }
 
-// ------------------------------------------------------------------------------------------------
-// The same update with the A operand in TENSOR MEMORY (tcgen05.mma with a TMEM A operand), selected with
-// HLSD_LL_TS=1.  Only B lives in shared memory (per 32-wide chunk 32 KB of writes + 48 KB of MMA reads
-// instead of 64 KB + 96 KB), which lets two CTAs share an SM.  Measured: the same 23.3 ms per batch of
-// 4096 as blk_ll_kernel.  Timing experiments on this kernel (operand loads removed: -4.6 ms, MMAs removed:
-// -1.3 ms, both: -5.6 ms of the update's 8.3 ms) show what bounds both versions: the 44 GB of panel
-// operands that the tiles of one step re-read from L2/HBM (6.3 TB/s), not shared memory and not the
-// tensor pipe.  The lever is therefore operand reuse: blk_ll2_kernel above (two row blocks per CTA).
-// Threads 0..127 own the A rows: thread = row keeps its 32 k-values of the chunk in registers
-// (global loads two chunks ahead) and writes them - hi part and lo part - straight into TMEM with
-// tcgen05.st.32x32b.x32 (lane = row, column = k).  Threads 128..255 stage B (raw = hi tile, lo tile)
-// in shared memory as before.  Per chunk: 32 KB of shared-memory writes + 48 KB of MMA reads.
-// TMEM: columns 0..127 accumulator, 128..255 two A buffers of (32 hi + 32 lo) columns.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                             uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-struct LlTsSmem {
-    static constexpr int kTile = 128 * 32 * 4;  // one B chunk: 128 rows x 32 k
-    static constexpr int kRaw = 0;              // [2] raw fp32 = tf32 hi operand
-    static constexpr int kLo = 2 * kTile;       // [2] lo operand
-    static constexpr int kBar = 4 * kTile;      // two mbarriers (the epilogue stage reuses the 64 KB below)
-    static constexpr int kTmemPtr = kBar + 16;
-    static constexpr int kTotal = kBar + 32 + 1024;
-};
-
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
-
-// 256 threads, 64 KB of shared memory, 256 TMEM columns: TWO CTAs per SM, so that one tile's prologue (first
-// loads at full DRAM latency) and epilogue (C tile, TMEM read-out, store) overlap the other's MMAs.
-constexpr int kLlTsThreads = 256;
-
-__global__ void __launch_bounds__(kLlTsThreads, 2)
-blk_ll_ts_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LlTsSmem::kBar);
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + LlTsSmem::kTmemPtr);
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int r = q + blockIdx.x;
-    float* Lb = L + (long)blockIdx.y * n * n;
-    const float* Sb = S + (long)blockIdx.y * n * n;
-    const float* Arows = Lb + (long)r * NB * n;  // finished panels 0 .. q-1 of block row r
-    const float* Brows = Lb + (long)q * NB * n;  // ... and of block row q
-    const int C = 4 * q;                         // 32-wide K chunks
-
-    if (warp == 0) tmem_alloc(tmem_ptr, 256);
-    if (t == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        fence_mbar_init();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_d = *tmem_ptr;
-
-    const bool a_side = t < 128;  // warp-uniform role
-    // A side (warps 0..3): thread = row = TMEM lane, the 32 k-values of a chunk
-    const float* aptr = Arows + (long)t * n;
-    const uint32_t a_taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + 128u;
-    // B side (warps 4..7): 1024 16-byte pieces per chunk, 8 per thread
-    const int tb = t - 128;
-    float4 buf[2][8];
-    auto gload = [&](int c, float4 (&b)[8]) {
-        if (c < C) {
-            if (a_side) {
-#pragma unroll
-                for (int it = 0; it < 8; it++) b[it] = __ldg(reinterpret_cast<const float4*>(aptr + c * 32) + it);
-            } else {
-#pragma unroll
-                for (int it = 0; it < 8; it++) {
-                    const int idx = it * 128 + tb, row = idx >> 3, c4 = idx & 7;
-                    b[it] = __ldg(reinterpret_cast<const float4*>(Brows + (long)row * n + c * 32 + c4 * 4));
-                }
-            }
-        }
-    };
-    auto step = [&](int c, float4 (&b)[8]) {
-        if (c >= 2) {  // MMAs of chunk c-2 are done: the TMEM and shared-memory buffers of this parity are free
-            mbar_wait(&bars[c & 1], (uint32_t)(((c - 2) >> 1) & 1));
-            tc_fence_after();
-        }
-        unsigned char* rb = smem + LlTsSmem::kRaw + (c & 1) * LlTsSmem::kTile;
-        unsigned char* lb = smem + LlTsSmem::kLo + (c & 1) * LlTsSmem::kTile;
-        if (a_side) {
-            const uint32_t base = a_taddr + (uint32_t)((c & 1) * 64);
-            uint32_t w[32];
-#pragma unroll
-            for (int it = 0; it < 8; it++) {
-                w[4 * it] = __float_as_uint(b[it].x) & 0xffffe000u;
-                w[4 * it + 1] = __float_as_uint(b[it].y) & 0xffffe000u;
-                w[4 * it + 2] = __float_as_uint(b[it].z) & 0xffffe000u;
-                w[4 * it + 3] = __float_as_uint(b[it].w) & 0xffffe000u;
-            }
-            tmem_st32(base, w);
-#pragma unroll
-            for (int it = 0; it < 8; it++) {
-                const float4 l = lo_of(b[it]);
-                w[4 * it] = __float_as_uint(l.x), w[4 * it + 1] = __float_as_uint(l.y);
-                w[4 * it + 2] = __float_as_uint(l.z), w[4 * it + 3] = __float_as_uint(l.w);
-            }
-            tmem_st32(base + 32u, w);
-            gload(c + 2, b);
-            tmem_wait_st();
-        } else {
-#pragma unroll
-            for (int it = 0; it < 8; it++) {
-                const int idx = it * 128 + tb, row = idx >> 3, c4 = idx & 7;
-                const int off = row * 128 + ((c4 ^ (row & 7)) << 4);
-                *reinterpret_cast<float4*>(rb + off) = b[it];
-                *reinterpret_cast<float4*>(lb + off) = lo_of(b[it]);
-            }
-            gload(c + 2, b);
-            fence_async_smem();
-        }
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (t == 0) {
-            const uint64_t dBhi = make_sw128_desc(smem_u32(rb)), dBlo = make_sw128_desc(smem_u32(lb));
-            const uint32_t a_hi = tmem_d + 128u + (uint32_t)((c & 1) * 64), a_lo = a_hi + 32u;
-#pragma unroll
-            for (int kk = 0; kk < 4; kk++) {
-                const uint64_t adv = (uint64_t)((kk * 32) >> 4);
-                const uint32_t first = (c == 0 && kk == 0) ? 0u : 1u;
-                umma_tf32_ts(tmem_d, a_lo + kk * 8, dBhi + adv, kIdescTf32, first);
-                umma_tf32_ts(tmem_d, a_hi + kk * 8, dBlo + adv, kIdescTf32, 1u);
-                umma_tf32_ts(tmem_d, a_hi + kk * 8, dBhi + adv, kIdescTf32, 1u);
-            }
-            umma_commit(&bars[c & 1]);
-        }
-    };
-    gload(0, buf[0]);
-    gload(1, buf[1]);
-    for (int c = 0; c < C; c += 2) {  // C = 4 q is even
-        step(c, buf[0]);
-        step(c + 1, buf[1]);
-    }
-    // the C tile (from A) is fetched while the last chunks are still being multiplied
-    const long coff = (long)r * NB * n + (long)q * NB;
-    constexpr int kRowsPerWarp = 128 / (kLlTsThreads / 32);
-    float4 cv[kRowsPerWarp];
-#pragma unroll
-    for (int rr = 0; rr < kRowsPerWarp; rr++)
-        cv[rr] = *(reinterpret_cast<const float4*>(Sb + coff + (long)(warp * kRowsPerWarp + rr) * n) + lane);
-    mbar_wait(&bars[(C - 2) & 1], (uint32_t)(((C - 2) >> 1) & 1));
-    mbar_wait(&bars[(C - 1) & 1], (uint32_t)(((C - 1) >> 1) & 1));
-    tc_fence_after();
-    {
-        float* stage = reinterpret_cast<float*>(smem);
-        const int drow = (warp & 3) * 32 + lane;  // accumulator row = TMEM lane (warp % 4 selects the lane quarter)
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int col = (warp >> 2) * 64 + h * 32;
-            float acc[32];
-            tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col, acc);
-#pragma unroll
-            for (int qq = 0; qq < 8; qq++) {
-                const int c4 = (col >> 2) + qq;
-                *reinterpret_cast<float4*>(stage + drow * 128 + ((c4 ^ (drow & 7)) << 2)) =
-                    make_float4(acc[4 * qq], acc[4 * qq + 1], acc[4 * qq + 2], acc[4 * qq + 3]);
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int rr = 0; rr < kRowsPerWarp; rr++) {
-            const int row = warp * kRowsPerWarp + rr;
-            const float4 d = *reinterpret_cast<const float4*>(stage + row * 128 + ((lane ^ (row & 7)) << 2));
-            float4 v = cv[rr];
-            v.x -= d.x, v.y -= d.y, v.z -= d.z, v.w -= d.w;
-            *(reinterpret_cast<float4*>(Lb + coff + (long)row * n) + lane) = v;
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_d, 256);
-}
-
 // left-looking driver: per block column q: update (if q > 0), diagonal block, TRSM
 static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int n, long batch, cudaStream_t st) {
-    cudaFuncSetAttribute(blk_mma_kernel<MMA_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
-    cudaFuncSetAttribute(blk_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LlSmem::kTotal);
-    cudaFuncSetAttribute(blk_ll_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LlTsSmem::kTotal);
-    cudaFuncSetAttribute(blk_ll2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Ll2Smem::kTotal);
-    cudaFuncSetAttribute(blk_diag_kernel<DIAG_CHOL_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
-    // HLSD_LL_TS (environment): update kernel variant.  2 (default) = two row blocks per CTA, 0 = one tile per
-    // CTA, 1 = one tile per CTA with the A operand in tensor memory.  Measured per batch of 4096 1024x1024
-    // matrices: 21.5 / 23.3 / 23.3 ms.
-    static int ll_ts = -1;
-    if (ll_ts < 0) {
-        const char* ev = getenv("HLSD_LL_TS");
-        ll_ts = ev ? atoi(ev) : 2;
-    }
+    cudaError_t e;
+    if ((e = ensure_dynamic_smem(blk_mma_kernel, MmaSmem::kTotal)) != cudaSuccess) return e;
+    if ((e = ensure_dynamic_smem(blk_ll2_kernel, Ll2Smem::kTotal)) != cudaSuccess) return e;
+    if ((e = ensure_dynamic_smem(blk_diag_kernel<DIAG_CHOL_INV>, kDiagSmem)) != cudaSuccess) return e;
     const int panels = n / NB;
     const unsigned nb = (unsigned)batch;
     blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, nb), 256, 0, st>>>(L, n);
@@ -1018,15 +619,13 @@ static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int
         const int mt = panels - q - 1;
         const float* src = (q == 0) ? A : L;  // where block column q currently lives
         if (q > 0) {
-            if (ll_ts == 1) blk_ll_ts_kernel<<<dim3(panels - q, nb), kLlTsThreads, LlTsSmem::kTotal, st>>>(A, L, n, q);
-            else if (ll_ts == 2) blk_ll2_kernel<<<dim3((panels - q + 1) / 2, nb), 512, Ll2Smem::kTotal, st>>>(A, L, n, q);
-            else blk_ll_kernel<<<dim3(panels - q, nb), kLlThreads, LlSmem::kTotal, st>>>(A, L, n, q);
+            blk_ll2_kernel<<<dim3((panels - q + 1) / 2, nb), 512, Ll2Smem::kTotal, st>>>(A, L, n, q);
             count_launch();
         }
         blk_diag_kernel<DIAG_CHOL_INV><<<nb, 512, kDiagSmem, st>>>(src, L, W, n, o);
         count_launch();
         if (mt > 0) {
-            blk_mma_kernel<MMA_TRSM><<<dim3(mt, nb), 256, MmaSmem::kTotal, st>>>(src, L, W, n, o);
+            blk_mma_kernel<<<dim3(mt, nb), 256, MmaSmem::kTotal, st>>>(src, L, W, n, o);
             count_launch();
         }
     }
@@ -1035,71 +634,29 @@ static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int
 
 // ------------------------------------------------------------------------------------------------
 // Bit-identical Cholesky of 128 x 128 matrices (right-looking designs): the register-tiled diagonal-block
-// kernel in exact arithmetic, one CTA per matrix.
-cudaError_t cholesky128_exact(const float* A, float* L, long batch, cudaStream_t st) {
-    cudaFuncSetAttribute(blk_diag_kernel<DIAG_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
+// kernel in exact arithmetic, one CTA per matrix (fused != 0: with the contraction HLSD_FLAG_FUSED allows).
+cudaError_t cholesky128_exact(const float* A, float* L, long batch, int fused, cudaStream_t st) {
+    auto kern = fused ? blk_diag_kernel<DIAG_EXACT, true> : blk_diag_kernel<DIAG_EXACT, false>;
+    cudaError_t e = ensure_dynamic_smem(kern, kDiagSmem);
+    if (e != cudaSuccess) return e;
     for (long b0 = 0; b0 < batch; b0 += 1 << 20) {
         const long cnt = std::min<long>(batch - b0, 1 << 20);
-        blk_diag_kernel<DIAG_EXACT><<<(unsigned)cnt, 512, kDiagSmem, st>>>(A + b0 * NB * NB, L + b0 * NB * NB, nullptr, NB, 0);
+        kern<<<(unsigned)cnt, 512, kDiagSmem, st>>>(A + b0 * NB * NB, L + b0 * NB * NB, nullptr, NB, 0);
         count_launch();
     }
     return cudaGetLastError();
 }
 
-// The workspaces come from the stream-ordered allocator; keep what it has reserved between calls
-// (the default pool hands memory back to the driver at every synchronisation point).
-static void keep_pool_memory() {
-    static thread_local int done_for = -1;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t keep = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    done_for = dev;
-}
-
 cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int use_tensor, cudaStream_t st) {
-    keep_pool_memory();
     if (n % NB != 0 || n < 2 * NB || !use_tensor) return cudaErrorNotSupported;
     if ((((uintptr_t)A | (uintptr_t)L) & 15) != 0) return cudaErrorNotSupported;
     if (batch == 0) return cudaSuccess;
     if (batch > 65535) return cudaErrorNotSupported;
-    cudaError_t e;
-    float* W = nullptr;
-    if ((e = cudaMallocAsync(&W, sizeof(float) * (size_t)batch * NB * NB, st)) != cudaSuccess) return e;
-    cudaFuncSetAttribute(blk_mma_kernel<MMA_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
-    cudaFuncSetAttribute(blk_mma_kernel<MMA_SYRK>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
-    cudaFuncSetAttribute(blk_diag_kernel<DIAG_CHOL_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
-    static int right_looking = -1;  // HLSD_CHOL_RIGHT_LOOKING=1 (environment): the per-panel SYRK variant
-    if (right_looking < 0) {
-        const char* ev = getenv("HLSD_CHOL_RIGHT_LOOKING");
-        right_looking = ev ? atoi(ev) : 0;
-    }
-    if (!right_looking) {
-        e = cholesky_left_looking(A, L, W, n, batch, st);
-        cudaFreeAsync(W, st);
-        return e;
-    }
-    const int panels = n / NB;
-    blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, (unsigned)batch), 256, 0, st>>>(L, n);
-    count_launch();
-    for (int p = 0; p < panels; p++) {
-        const int o = p * NB;
-        const int mt = panels - p - 1;  // 128-row blocks below the diagonal block
-        const float* src = (p == 0) ? A : L;
-        blk_diag_kernel<DIAG_CHOL_INV><<<(unsigned)batch, 512, kDiagSmem, st>>>(src, L, W, n, o);
-        count_launch();
-        if (mt > 0) {
-            blk_mma_kernel<MMA_TRSM><<<dim3(mt, (unsigned)batch), 256, MmaSmem::kTotal, st>>>(src, L, W, n, o);
-            count_launch();
-            blk_mma_kernel<MMA_SYRK><<<dim3(mt * (mt + 1) / 2, (unsigned)batch), 256, MmaSmem::kTotal, st>>>(src, L, W, n, o);
-            count_launch();
-        }
-    }
-    e = cudaGetLastError();
-    cudaFreeAsync(W, st);
+    float* W = nullptr;  // inverted diagonal blocks of the current block column, one per matrix
+    cudaError_t e = ws_alloc(reinterpret_cast<void**>(&W), sizeof(float) * (size_t)batch * NB * NB, st);
+    if (e != cudaSuccess) return e;
+    e = cholesky_left_looking(A, L, W, n, batch, st);
+    ws_free(W, st);
     return e;
 }
 
@@ -1552,20 +1109,23 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
     if ((((uintptr_t)A | (uintptr_t)L | (uintptr_t)U) & 15) != 0) return cudaErrorNotSupported;
     if (batch == 0) return cudaSuccess;
     if (batch > 65535) return cudaErrorNotSupported;
-    keep_pool_memory();
     cudaError_t e;
-    float *Winv = nullptr, *T0 = nullptr, *T1 = nullptr;
-    if ((e = cudaMallocAsync(&Winv, sizeof(float) * (size_t)batch * NB * NB, st)) != cudaSuccess) return e;
-    if ((e = cudaMallocAsync(&T0, sizeof(float) * (size_t)batch * n * NB, st)) != cudaSuccess) return e;
-    if ((e = cudaMallocAsync(&T1, sizeof(float) * (size_t)batch * n * NB, st)) != cudaSuccess) return e;
     const size_t unswap_smem = (size_t)2 * NB * (NB + 1) * sizeof(float) + (size_t)n * sizeof(int);
-    cudaFuncSetAttribute(lu_unswap_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)unswap_smem);
-    cudaFuncSetAttribute(blk_diag_kernel<DIAG_INV_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
-    cudaFuncSetAttribute(gemm_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
-    cudaFuncSetAttribute(gemm_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem::kTotal);
+    if ((e = ensure_dynamic_smem(lu_unswap_panel_kernel, unswap_smem)) != cudaSuccess) return e;
+    if ((e = ensure_dynamic_smem(blk_diag_kernel<DIAG_INV_ONLY>, kDiagSmem)) != cudaSuccess) return e;
+    if ((e = ensure_dynamic_smem(gemm_tile_kernel<0>, MmaSmem::kTotal)) != cudaSuccess) return e;
+    if ((e = ensure_dynamic_smem(gemm_tile_kernel<1>, MmaSmem::kTotal)) != cudaSuccess) return e;
+    // one workspace: W = inv(L11) per matrix, T0 = A12^T, T1 = U12^T
+    const size_t w_floats = (size_t)batch * NB * NB, t_floats = (size_t)batch * n * NB;
+    float* ws = nullptr;
+    if ((e = ws_alloc(reinterpret_cast<void**>(&ws), sizeof(float) * (w_floats + 2 * t_floats), st)) != cudaSuccess) return e;
+    float *Winv = ws, *T0 = ws + w_floats, *T1 = T0 + t_floats;
     const unsigned nb = (unsigned)batch;
     const long nn = (long)n * n;
-    if ((e = cudaMemcpyAsync(U, A, sizeof(float) * (size_t)batch * nn, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(U, A, sizeof(float) * (size_t)batch * nn, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) {
+        ws_free(ws, st);
+        return e;
+    }
     const int panels = n / NB;
     blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, nb), 256, 0, st>>>(L, n);
     count_launch();
@@ -1606,9 +1166,7 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
         count_launch();
     }
     e = cudaGetLastError();
-    cudaFreeAsync(Winv, st);
-    cudaFreeAsync(T0, st);
-    cudaFreeAsync(T1, st);
+    ws_free(ws, st);
     return e;
 }
 

@@ -3,7 +3,11 @@
 // CUDA kernel launch or fails.
 #include <atomic>
 #include <cstdio>
+#include <map>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "kernels.h"
@@ -22,6 +26,60 @@ int sm_count() {
         cached_dev = dev;
     }
     return cached;
+}
+
+// kernel attribute cache: (kernel, device) -> largest dynamic shared-memory size granted so far
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> granted;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = granted[{kernel, dev}];
+    if (have >= bytes && have != 0) return cudaSuccess;
+    if (bytes <= 48 * 1024 && have == 0) {  // the default limit already covers it
+        have = 48 * 1024;
+        return cudaSuccess;
+    }
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
+
+// library-owned stream-ordered memory pool per device (workspaces of the blocked paths); memory stays reserved
+// between calls (release threshold = max) until hlsd_release_workspace() trims it
+static std::mutex g_pool_mu;
+static std::map<int, cudaMemPool_t> g_pools;
+static cudaError_t device_pool(cudaMemPool_t* out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    auto it = g_pools.find(dev);
+    if (it == g_pools.end()) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool;
+        if ((e = cudaMemPoolCreate(&pool, &props)) != cudaSuccess) return e;
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        it = g_pools.emplace(dev, pool).first;
+    }
+    *out = it->second;
+    return cudaSuccess;
+}
+cudaError_t ws_alloc(void** p, size_t bytes, cudaStream_t st) {
+    cudaMemPool_t pool;
+    cudaError_t e = device_pool(&pool);
+    if (e != cudaSuccess) return e;
+    return cudaMallocFromPoolAsync(p, bytes ? bytes : 16, pool, st);
+}
+void ws_free(void* p, cudaStream_t st) {
+    if (p) cudaFreeAsync(p, st);
 }
 
 static thread_local std::string g_err = "";
@@ -61,22 +119,29 @@ static bool qr_variant(int design, int* variant) {
     }
 }
 
-static int check_path(int flags, int* path) {
-    if (flags & ~HLSD_PATH_MASK) return fail(HLSD_ERR_INVALID, "unknown flag bits");
+static int check_flags(int flags, int* path, bool* exact, bool* fused) {
+    if (flags & ~(HLSD_PATH_MASK | HLSD_FLAG_MASK)) return fail(HLSD_ERR_INVALID, "unknown flag bits");
     *path = flags & HLSD_PATH_MASK;
+    *exact = (flags & HLSD_FLAG_EXACT) != 0;
+    *fused = (flags & HLSD_FLAG_FUSED) != 0;
     if (*path > HLSD_PATH_TENSOR) return fail(HLSD_ERR_INVALID, "unknown kernel path");
+    if (*exact && *fused) return fail(HLSD_ERR_INVALID, "HLSD_FLAG_EXACT and HLSD_FLAG_FUSED exclude each other");
+    if (*exact && *path == HLSD_PATH_TENSOR) return fail(HLSD_ERR_INVALID, "HLSD_FLAG_EXACT excludes HLSD_PATH_TENSOR");
     return 0;
 }
 
 // ---- device entry points ----------------------------------------------------------------------
 static int chol_dev(const float* A, float* L, int n, int64_t batch, int design, int flags, cudaStream_t st) {
     int variant, path;
+    bool exact, fused;
     if (!A || !L) return fail(HLSD_ERR_INVALID, "null pointer");
     if (n < 1 || batch < 0) return fail(HLSD_ERR_INVALID, "n must be >= 1 and batch >= 0");
     if (!chol_variant(design, &variant)) return fail(HLSD_ERR_INVALID, "unknown Cholesky design");
-    if (int rc = check_path(flags, &path)) return rc;
-    // large right-looking problems go to the blocked tensor-core path unless a path was forced
-    if (path == HLSD_PATH_AUTO && variant == 0 && n >= 256 && n % 128 == 0 && (((uintptr_t)A | (uintptr_t)L) & 15) == 0)
+    if (int rc = check_flags(flags, &path, &exact, &fused)) return rc;
+    // large right-looking problems go to the blocked tensor-core path unless a path was forced or the caller
+    // asked for the csim's bits (HLSD_FLAG_EXACT)
+    if (path == HLSD_PATH_AUTO && !exact && variant == 0 && n >= 256 && n % 128 == 0 &&
+        (((uintptr_t)A | (uintptr_t)L) & 15) == 0)
         path = HLSD_PATH_TENSOR;
     if (path == HLSD_PATH_BLOCKED || path == HLSD_PATH_TENSOR) {
         if (variant != 0) return fail(HLSD_ERR_UNSUPPORTED, "blocked Cholesky implements the right-looking designs only");
@@ -90,7 +155,7 @@ static int chol_dev(const float* A, float* L, int n, int64_t batch, int design, 
         if (e != cudaSuccess) return cuda_fail(e, "cholesky_blocked");
         return 0;
     }
-    cudaError_t e = cholesky_exact(A, L, n, (long)batch, variant, path, st);
+    cudaError_t e = cholesky_exact(A, L, n, (long)batch, variant, path, fused, st);
     if (e == cudaErrorInvalidValue) return fail(HLSD_ERR_UNSUPPORTED, "requested kernel path cannot serve this size/alignment");
     if (e != cudaSuccess) return cuda_fail(e, "cholesky");
     return 0;
@@ -99,11 +164,12 @@ static int chol_dev(const float* A, float* L, int n, int64_t batch, int design, 
 static int lu_dev(const float* A, float* L, float* U, int32_t* P, int n, int64_t batch, int design, int flags,
                   cudaStream_t st) {
     int pivoting, path;
+    bool exact, fused;
     if (!A || !L || !U || !P) return fail(HLSD_ERR_INVALID, "null pointer");
     if (n < 1 || batch < 0) return fail(HLSD_ERR_INVALID, "n must be >= 1 and batch >= 0");
     if (!lu_pivoting(design, &pivoting)) return fail(HLSD_ERR_INVALID, "unknown LU design");
-    if (int rc = check_path(flags, &path)) return rc;
-    if (path == HLSD_PATH_AUTO && pivoting && n >= 256 && n <= 1024 && n % 128 == 0 &&
+    if (int rc = check_flags(flags, &path, &exact, &fused)) return rc;
+    if (path == HLSD_PATH_AUTO && !exact && pivoting && n >= 256 && n <= 1024 && n % 128 == 0 &&
         (((uintptr_t)A | (uintptr_t)L | (uintptr_t)U) & 15) == 0)
         path = HLSD_PATH_TENSOR;
     if (path == HLSD_PATH_BLOCKED) return fail(HLSD_ERR_UNSUPPORTED, "HLSD_PATH_BLOCKED (SIMT trailing update) is not built; use HLSD_PATH_TENSOR or HLSD_PATH_GLOBAL");
@@ -119,7 +185,7 @@ static int lu_dev(const float* A, float* L, float* U, int32_t* P, int n, int64_t
         if (e != cudaSuccess) return cuda_fail(e, "lu_blocked");
         return 0;
     }
-    cudaError_t e = lu_exact(A, L, U, P, n, (long)batch, pivoting, path, st);
+    cudaError_t e = lu_exact(A, L, U, P, n, (long)batch, pivoting, path, fused, st);
     if (e == cudaErrorInvalidValue) return fail(HLSD_ERR_UNSUPPORTED, "requested kernel path cannot serve this size/alignment");
     if (e != cudaSuccess) return cuda_fail(e, "lu");
     return 0;
@@ -128,14 +194,15 @@ static int lu_dev(const float* A, float* L, float* U, int32_t* P, int n, int64_t
 static int qr_dev(const float* A, float* Q, float* R, int rows, int cols, int64_t batch, int design, int flags,
                   cudaStream_t st) {
     int variant, path;
+    bool exact, fused;
     if (!A || !Q || !R) return fail(HLSD_ERR_INVALID, "null pointer");
     // the reference's top() rejects ROWS < COLS (qr_v2.1/model4x4/qr.cpp:325-332)
     if (cols < 1 || rows < cols || batch < 0) return fail(HLSD_ERR_INVALID, "need rows >= cols >= 1 and batch >= 0");
     if (!qr_variant(design, &variant)) return fail(HLSD_ERR_INVALID, "unknown QR design");
-    if (int rc = check_path(flags, &path)) return rc;
+    if (int rc = check_flags(flags, &path, &exact, &fused)) return rc;
     if (path == HLSD_PATH_BLOCKED || path == HLSD_PATH_TENSOR)
         return fail(HLSD_ERR_UNSUPPORTED, "Givens QR has no blocked path");
-    cudaError_t e = qr_exact(A, Q, R, rows, cols, (long)batch, variant, path, st);
+    cudaError_t e = qr_exact(A, Q, R, rows, cols, (long)batch, variant, path, fused, st);
     if (e == cudaErrorInvalidValue) return fail(HLSD_ERR_UNSUPPORTED, "requested kernel path cannot serve this size/alignment");
     if (e != cudaSuccess) return cuda_fail(e, "qr");
     return 0;
@@ -150,11 +217,14 @@ struct Buf {
     size_t bytes_per_matrix;
 };
 
-// Per-thread, per-device staging workspace kept across calls: three streams and, per stream, one
-// growable device buffer per argument.  (cudaMalloc / cudaFree / stream creation per call cost more
-// than the whole factorisation of a small batch.)  Released by hlsd_release_workspace().
+// Staging workspace: three streams and, per stream, one growable device buffer per argument.  (cudaMalloc /
+// cudaFree / stream creation per call cost more than the whole factorisation of a small batch.)  Workspaces live
+// in a process-wide pool keyed by device: a call takes one (or creates it), gives it back when it returns, and
+// hlsd_release_workspace() frees the idle ones - nothing is tied to the calling thread, so short-lived threads
+// leak nothing.  Buffers above kKeepBytes are dropped when the call ends instead of being kept.
 struct Workspace {
     static constexpr int kStreams = 3;
+    static constexpr size_t kKeepBytes = (size_t)256 << 20;
     int device = -1;
     cudaStream_t st[kStreams] = {};
     std::vector<void*> buf[kStreams];
@@ -168,19 +238,23 @@ struct Workspace {
             if (st[i]) cudaStreamDestroy(st[i]);
             st[i] = nullptr;
         }
-        device = -1;
+    }
+    void shrink() {
+        for (int i = 0; i < kStreams; i++)
+            for (size_t j = 0; j < buf[i].size(); j++)
+                if (cap[i][j] > kKeepBytes) {
+                    cudaFree(buf[i][j]);
+                    buf[i][j] = nullptr;
+                    cap[i][j] = 0;
+                }
     }
     cudaError_t prepare(int slot, const std::vector<size_t>& bytes) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
-        if (dev != device) {
-            release();
-            device = dev;
-        }
+        cudaError_t e;
         if (!st[slot] && (e = cudaStreamCreateWithFlags(&st[slot], cudaStreamNonBlocking)) != cudaSuccess) return e;
-        buf[slot].resize(bytes.size(), nullptr);
-        cap[slot].resize(bytes.size(), 0);
+        if (buf[slot].size() < bytes.size()) {
+            buf[slot].resize(bytes.size(), nullptr);
+            cap[slot].resize(bytes.size(), 0);
+        }
         for (size_t i = 0; i < bytes.size(); i++)
             if (cap[slot][i] < bytes[i]) {
                 if (buf[slot][i]) cudaFree(buf[slot][i]);
@@ -191,27 +265,78 @@ struct Workspace {
             }
         return cudaSuccess;
     }
-    ~Workspace() {}  // the CUDA context may already be gone at thread exit: leak rather than crash
 };
-static thread_local Workspace g_ws;
+static std::mutex g_ws_mu;
+static std::multimap<int, Workspace*> g_ws_idle;  // device -> idle workspaces
+
+static Workspace* ws_acquire(int dev) {
+    {
+        std::lock_guard<std::mutex> lock(g_ws_mu);
+        auto it = g_ws_idle.find(dev);
+        if (it != g_ws_idle.end()) {
+            Workspace* w = it->second;
+            g_ws_idle.erase(it);
+            return w;
+        }
+    }
+    Workspace* w = new Workspace();
+    w->device = dev;
+    return w;
+}
+static void ws_giveback(Workspace* w) {
+    w->shrink();
+    std::lock_guard<std::mutex> lock(g_ws_mu);
+    g_ws_idle.emplace(w->device, w);
+}
+static void ws_release_idle() {
+    std::vector<Workspace*> all;
+    {
+        std::lock_guard<std::mutex> lock(g_ws_mu);
+        for (auto& kv : g_ws_idle) all.push_back(kv.second);
+        g_ws_idle.clear();
+    }
+    int cur = 0;
+    const bool have_cur = cudaGetDevice(&cur) == cudaSuccess;
+    for (Workspace* w : all) {
+        if (cudaSetDevice(w->device) == cudaSuccess) w->release();
+        delete w;
+    }
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        for (auto& kv : g_pools) cudaMemPoolTrimTo(kv.second, 0);
+    }
+    if (have_cur) cudaSetDevice(cur);
+}
+
+// Chunk size of the staging pipeline: about kChunkBytes of arguments per chunk, at least one matrix, and - so that
+// the copy-in of chunk i+1, the kernels of chunk i and the copy-out of chunk i-1 can overlap - no more than a
+// third of the batch when the batch is large enough to be worth splitting.  Every chunk is copied to the BASE of
+// its staging buffers (cudaMalloc alignment), so chunk starts need no alignment of their own.
+static int64_t staging_chunk(int64_t batch, size_t per_matrix) {
+    const size_t kChunkBytes = (size_t)64 << 20, kMinSplitBytes = (size_t)8 << 20;
+    int64_t chunk = (int64_t)(kChunkBytes / (per_matrix ? per_matrix : 1));
+    if (chunk < 1) chunk = 1;
+    if (chunk > batch) chunk = batch;
+    if (chunk == batch && batch >= 3 && (size_t)batch * per_matrix >= 3 * kMinSplitBytes) chunk = (batch + 2) / 3;
+    return chunk;
+}
 
 template <typename LaunchF>
 static int run_host_pipeline(int64_t batch, std::vector<Buf> bufs, LaunchF launch) {
     if (batch == 0) return 0;
     size_t per_matrix = 0;
     for (auto& b : bufs) per_matrix += b.bytes_per_matrix;
-    const size_t kChunkBytes = (size_t)64 << 20;
-    int64_t chunk = (int64_t)(kChunkBytes / (per_matrix ? per_matrix : 1));
-    if (chunk < 1) chunk = 1;
-    if (chunk > batch) chunk = batch;
-    chunk = (chunk + 31) / 32 * 32;  // keep chunk starts 16-byte aligned for every element size used here
+    const int64_t chunk = staging_chunk(batch, per_matrix);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    Workspace* ws = ws_acquire(dev);
     int rc = 0;
-    cudaError_t e = cudaSuccess;
     int used = 0;
     std::vector<size_t> bytes;
     for (auto& b : bufs) bytes.push_back(b.bytes_per_matrix * (size_t)chunk);
     for (; used < Workspace::kStreams && used * chunk < batch; used++)
-        if ((e = g_ws.prepare(used, bytes)) != cudaSuccess) {
+        if ((e = ws->prepare(used, bytes)) != cudaSuccess) {
             rc = cuda_fail(e, "staging workspace");
             break;
         }
@@ -219,29 +344,73 @@ static int run_host_pipeline(int64_t batch, std::vector<Buf> bufs, LaunchF launc
         int slot = 0;
         for (int64_t m0 = 0; m0 < batch && !rc; m0 += chunk, slot = (slot + 1) % used) {
             const int64_t cnt = (batch - m0 < chunk) ? batch - m0 : chunk;
-            cudaStream_t st = g_ws.st[slot];
-            std::vector<void*>& dev = g_ws.buf[slot];
+            cudaStream_t st = ws->st[slot];
+            std::vector<void*>& dbuf = ws->buf[slot];
             for (size_t i = 0; i < bufs.size() && !rc; i++)
                 if (bufs[i].host_in) {
-                    e = cudaMemcpyAsync(dev[i], (const char*)bufs[i].host_in + bufs[i].bytes_per_matrix * (size_t)m0,
+                    e = cudaMemcpyAsync(dbuf[i], (const char*)bufs[i].host_in + bufs[i].bytes_per_matrix * (size_t)m0,
                                         bufs[i].bytes_per_matrix * (size_t)cnt, cudaMemcpyHostToDevice, st);
                     if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync H2D");
                 }
-            if (!rc) rc = launch(dev, cnt, st);
+            if (!rc) rc = launch(dbuf, cnt, st);
             for (size_t i = 0; i < bufs.size() && !rc; i++)
                 if (bufs[i].host_out) {
-                    e = cudaMemcpyAsync((char*)bufs[i].host_out + bufs[i].bytes_per_matrix * (size_t)m0, dev[i],
+                    e = cudaMemcpyAsync((char*)bufs[i].host_out + bufs[i].bytes_per_matrix * (size_t)m0, dbuf[i],
                                         bufs[i].bytes_per_matrix * (size_t)cnt, cudaMemcpyDeviceToHost, st);
                     if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H");
                 }
         }
     }
-    for (int i = 0; i < used; i++)
-        if (g_ws.st[i]) {
-            e = cudaStreamSynchronize(g_ws.st[i]);
+    for (int i = 0; i < Workspace::kStreams; i++)
+        if (ws->st[i]) {
+            e = cudaStreamSynchronize(ws->st[i]);
             if (e != cudaSuccess && !rc) rc = cuda_fail(e, "cudaStreamSynchronize");
         }
+    ws_giveback(ws);
     return rc;
+}
+
+// One host batch over several devices: contiguous balanced spans, one worker thread per device, each running
+// `span(first, count)` (a *_host call on its slice) after cudaSetDevice.  The first failure is reported.
+template <typename SpanF>
+static int run_multi(int64_t batch, const int* devices, int ndevices, SpanF span) {
+    std::vector<int> devs;
+    if (!devices) {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) return fail(HLSD_ERR_CUDA, "no CUDA device");
+        if (ndevices > 0 && ndevices < n) n = ndevices;
+        for (int i = 0; i < n; i++) devs.push_back(i);
+    } else {
+        if (ndevices < 1) return fail(HLSD_ERR_INVALID, "ndevices must be >= 1");
+        devs.assign(devices, devices + ndevices);
+    }
+    const int nd = (int)devs.size();
+    std::vector<int> rcs(nd, 0);
+    std::vector<std::string> errs(nd);
+    std::vector<std::thread> workers;
+    const int64_t base = batch / nd, extra = batch % nd;
+    int64_t first = 0;
+    for (int i = 0; i < nd; i++) {
+        const int64_t cnt = base + (i < extra ? 1 : 0);
+        if (cnt > 0 || i == 0)
+            workers.emplace_back([&, i, first, cnt]() {
+                cudaError_t e = cudaSetDevice(devs[i]);
+                if (e != cudaSuccess) {
+                    rcs[i] = cuda_fail(e, "cudaSetDevice");
+                } else {
+                    rcs[i] = span(first, cnt);
+                }
+                if (rcs[i]) errs[i] = g_err;  // g_err is thread-local: carry the message to the caller's thread
+            });
+        first += cnt;
+    }
+    for (auto& w : workers) w.join();
+    for (int i = 0; i < nd; i++)
+        if (rcs[i]) {
+            g_err = "device " + std::to_string(devs[i]) + ": " + errs[i];
+            return rcs[i];
+        }
+    return 0;
 }
 
 }  // namespace hlsd
@@ -307,7 +476,42 @@ void hlsd_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
-void hlsd_release_workspace(void) { g_ws.release(); }
+void hlsd_release_workspace(void) { ws_release_idle(); }
+
+int hlsd_cholesky_host_multi(const float* A, float* L, int n, int64_t batch, int design, int flags,
+                             const int* devices, int ndevices) {
+    if (!A || !L) return fail(HLSD_ERR_INVALID, "null pointer");
+    if (n < 1 || batch < 0) return fail(HLSD_ERR_INVALID, "n must be >= 1 and batch >= 0");
+    const size_t mm = (size_t)n * n;
+    return run_multi(batch, devices, ndevices, [&](int64_t first, int64_t cnt) {
+        return hlsd_cholesky_host(A + first * mm, L + first * mm, n, cnt, design, flags);
+    });
+}
+int hlsd_lu_host_multi(const float* A, float* L, float* U, int32_t* P, int n, int64_t batch, int design, int flags,
+                       const int* devices, int ndevices) {
+    if (!A || !L || !U || !P) return fail(HLSD_ERR_INVALID, "null pointer");
+    if (n < 1 || batch < 0) return fail(HLSD_ERR_INVALID, "n must be >= 1 and batch >= 0");
+    const size_t mm = (size_t)n * n;
+    return run_multi(batch, devices, ndevices, [&](int64_t first, int64_t cnt) {
+        return hlsd_lu_host(A + first * mm, L + first * mm, U + first * mm, P + first * n, n, cnt, design, flags);
+    });
+}
+int hlsd_qr_host_multi(const float* A, float* Q, float* R, int rows, int cols, int64_t batch, int design, int flags,
+                       const int* devices, int ndevices) {
+    if (!A || !Q || !R) return fail(HLSD_ERR_INVALID, "null pointer");
+    if (cols < 1 || rows < cols || batch < 0) return fail(HLSD_ERR_INVALID, "need rows >= cols >= 1 and batch >= 0");
+    const size_t am = (size_t)rows * cols, qm = (size_t)rows * rows;
+    return run_multi(batch, devices, ndevices, [&](int64_t first, int64_t cnt) {
+        return hlsd_qr_host(A + first * am, Q + first * qm, R + first * am, rows, cols, cnt, design, flags);
+    });
+}
+
+int hlsd_selftest_copy_host(const void* in, void* out, size_t in_bytes, size_t out_bytes, int64_t units) {
+    if (!in || !out || units < 0 || in_bytes == 0 || out_bytes == 0)
+        return fail(HLSD_ERR_INVALID, "hlsd_selftest_copy_host: bad argument");
+    return run_host_pipeline(units, {{in, nullptr, in_bytes}, {nullptr, out, out_bytes}},
+                             [](std::vector<void*>&, int64_t, cudaStream_t) { return 0; });
+}
 
 int hlsd_set_device(int device) {
     cudaError_t e = cudaSetDevice(device);
@@ -321,11 +525,11 @@ int hlsd_device_count(void) {
 }
 int64_t hlsd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* hlsd_last_error(void) { return g_err.c_str(); }
-const char* hlsd_version(void) { return "hlsd 0.1 (sm_100a)"; }
+const char* hlsd_version(void) { return "hlsd 0.2 (sm_100a)"; }
 
-int hlsd_selftest_division(const float* num, const float* den, int64_t count, int64_t* out2, void* stream) {
-    if (!num || !den || !out2 || count < 0) return fail(HLSD_ERR_INVALID, "hlsd_selftest_division: bad argument");
-    cudaError_t e = hlsd::selftest_division(num, den, (long)count, reinterpret_cast<long long*>(out2), (cudaStream_t)stream);
+int hlsd_selftest_division(const float* num, const float* den, int64_t count, int64_t* out3, void* stream) {
+    if (!num || !den || !out3 || count < 0) return fail(HLSD_ERR_INVALID, "hlsd_selftest_division: bad argument");
+    cudaError_t e = hlsd::selftest_division(num, den, (long)count, reinterpret_cast<long long*>(out3), (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "selftest_division");
     return 0;
 }

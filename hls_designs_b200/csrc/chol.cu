@@ -6,14 +6,12 @@
 //   variant 1  "revised" root-free elimination + final scaling: cholesky_v2.2 (chol.cpp:28-207)
 //
 // Kernels:
-//   chol_tpm_kernel<N>   thread-per-matrix, N in {4, 8, 16}: each warp owns a shared-memory slab of
+//   chol_tpm_kernel<N>   thread-per-matrix, N in {4, 8}: each warp owns a shared-memory slab of
 //                        32 padded matrix slots filled by 1-D bulk async copies (TMA engine), each
 //                        thread factors its matrix entirely in registers and the slab is written
 //                        back with bulk stores.  HBM-bound (2*N*N*4 bytes per matrix).
 //   chol_group_kernel<G> G threads per matrix, matrix resident in shared memory: any N that fits.
 //   chol_global_kernel   one CTA per matrix, working in place in global memory/L2: any N (slow, exact).
-#include <cstdlib>
-
 #include "common.cuh"
 #include "kernels.h"
 
@@ -29,7 +27,7 @@ struct TpmCfg {
     static constexpr int kMatBytes = N * N * 4;
 };
 
-template <int N, int VARIANT>
+template <int N, int VARIANT, bool FUSED>
 __device__ __forceinline__ void chol_regs(float (&a)[N * (N + 1) / 2]) {
 #define T(i, j) ((i) * ((i) + 1) / 2 + (j))
     if constexpr (VARIANT == 0) {
@@ -42,7 +40,7 @@ __device__ __forceinline__ void chol_regs(float (&a)[N * (N + 1) / 2]) {
 #pragma unroll
             for (int i = k + 1; i < N; i++)
 #pragma unroll
-                for (int j = i; j < N; j++) a[T(j, i)] = xmsub(a[T(j, i)], a[T(j, k)], a[T(i, k)]);
+                for (int j = i; j < N; j++) a[T(j, i)] = msub<FUSED>(a[T(j, i)], a[T(j, k)], a[T(i, k)]);
         }
     } else {
 #pragma unroll
@@ -54,7 +52,7 @@ __device__ __forceinline__ void chol_regs(float (&a)[N * (N + 1) / 2]) {
 #pragma unroll
             for (int i = k + 1; i < N; i++)
 #pragma unroll
-                for (int j = i; j < N; j++) a[T(j, i)] = xmsub(a[T(j, i)], a[T(j, k)], m[i]);
+                for (int j = i; j < N; j++) a[T(j, i)] = msub<FUSED>(a[T(j, i)], a[T(j, k)], m[i]);
 #pragma unroll
             for (int i = k + 1; i < N; i++) a[T(i, k)] = m[i];
         }
@@ -69,7 +67,7 @@ __device__ __forceinline__ void chol_regs(float (&a)[N * (N + 1) / 2]) {
 #undef T
 }
 
-template <int N, int VARIANT, int WARPS>
+template <int N, int VARIANT, int WARPS, bool FUSED>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 chol_tpm_kernel(const float* __restrict__ A, float* __restrict__ L, long batch) {
     using Cfg = TpmCfg<N>;
@@ -119,7 +117,7 @@ chol_tpm_kernel(const float* __restrict__ A, float* __restrict__ L, long batch) 
                     for (int t = 0; t < 4; t++)
                         if (4 * q + t <= i) a[i * (i + 1) / 2 + 4 * q + t] = e[t];
                 }
-            chol_regs<N, VARIANT>(a);
+            chol_regs<N, VARIANT, FUSED>(a);
             float4* d4 = reinterpret_cast<float4*>(slot);
 #pragma unroll
             for (int i = 0; i < N; i++)
@@ -154,7 +152,7 @@ chol_tpm_kernel(const float* __restrict__ A, float* __restrict__ L, long batch) 
 // and the column is all-gathered by one shuffle per row (the "column update" stream).
 // Entries a[t][j] with j > row index are scratch (computed, never stored).
 // ------------------------------------------------------------------------------------------------
-template <int N, int R, int VARIANT, int WARPS>
+template <int N, int R, int VARIANT, int WARPS, bool FUSED>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 chol_rows_kernel(const float* __restrict__ A, float* __restrict__ L, long batch) {
     using Cfg = TpmCfg<N>;
@@ -245,7 +243,7 @@ chol_rows_kernel(const float* __restrict__ A, float* __restrict__ L, long batch)
                 const float lik = __shfl_sync(0xffffffffu, own[i / R], gbase + (i % R));
                 // rows j = t*R + r >= i  <=>  t >= i/R (the t == i/R case is scratch when r < i % R)
 #pragma unroll
-                for (int t = i / R; t < T; t++) a[t][i] = xmsub(a[t][i], a[t][k], lik);
+                for (int t = i / R; t < T; t++) a[t][i] = msub<FUSED>(a[t][i], a[t][k], lik);
             }
             if constexpr (VARIANT == 1) {
 #pragma unroll
@@ -432,24 +430,12 @@ chol_global_kernel(const float* __restrict__ A, float* __restrict__ L, float* __
 // ------------------------------------------------------------------------------------------------
 // host-side dispatch
 // ------------------------------------------------------------------------------------------------
-// HLSD_CHOL16 (environment, read once) selects the N=16 kernel for A/B measurements:
-//   "tpm" one thread per matrix (6 warps/SM), "r2" / "r4" (default): 2 / 4 lanes per matrix
-//   (measured 4739 / 5477 / 6017 GB/s of algorithmic traffic at batch 1M).
-static int chol16_mode() {
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("HLSD_CHOL16");
-        mode = !e ? 4 : (e[0] == 't' ? 1 : (e[1] == '2' ? 2 : 4));
-    }
-    return mode;
-}
-
-template <int N, int VARIANT, int WARPS>
+template <int N, int VARIANT, int WARPS, bool FUSED>
 static cudaError_t launch_tpm_w(const float* A, float* L, long batch, cudaStream_t st) {
     using Cfg = TpmCfg<N>;
     const size_t smem = (size_t)WARPS * Cfg::kSlabFloats * 4 + WARPS * sizeof(uint64_t);
-    auto kern = chol_tpm_kernel<N, VARIANT, WARPS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = chol_tpm_kernel<N, VARIANT, WARPS, FUSED>;
+    cudaError_t e = ensure_dynamic_smem(kern, smem);
     if (e != cudaSuccess) return e;
     const long num_slabs = (batch + 31) / 32;
     int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024) / (smem + 1024)));
@@ -459,13 +445,13 @@ static cudaError_t launch_tpm_w(const float* A, float* L, long batch, cudaStream
     return cudaGetLastError();
 }
 
-template <int N, int R, int VARIANT, int WARPS>
+template <int N, int R, int VARIANT, int WARPS, bool FUSED>
 static cudaError_t launch_rows(const float* A, float* L, long batch, cudaStream_t st) {
     using Cfg = TpmCfg<N>;
     constexpr int MPW = 32 / R;
     const size_t smem = (size_t)WARPS * MPW * Cfg::kSlot * 4 + WARPS * sizeof(uint64_t);
-    auto kern = chol_rows_kernel<N, R, VARIANT, WARPS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = chol_rows_kernel<N, R, VARIANT, WARPS, FUSED>;
+    cudaError_t e = ensure_dynamic_smem(kern, smem);
     if (e != cudaSuccess) return e;
     const long num_slabs = (batch + MPW - 1) / MPW;
     long grid = std::min<long>((num_slabs + WARPS - 1) / WARPS, (long)sm_count());
@@ -474,22 +460,20 @@ static cudaError_t launch_rows(const float* A, float* L, long batch, cudaStream_
     return cudaGetLastError();
 }
 
-template <int N, int VARIANT>
+template <int N, int VARIANT, bool FUSED>
 static cudaError_t launch_tpm(const float* A, float* L, long batch, cudaStream_t st) {
     if constexpr (N == 16) {
-        switch (chol16_mode()) {
-            case 1: return launch_tpm_w<N, VARIANT, 6>(A, L, batch, st);
-            case 2: return launch_rows<N, 2, VARIANT, 12>(A, L, batch, st);
-            default: return launch_rows<N, 4, VARIANT, 24>(A, L, batch, st);
-        }
+        // lanes per matrix, measured at batch 1M (GB/s of algorithmic traffic): 1 (6 warps/SM) 4739, 2 (12 warps) 5477,
+        // 4 (24 warps) 6017 -> 6305 after the division work of DESIGN.md 4.0
+        return launch_rows<N, 4, VARIANT, 24, FUSED>(A, L, batch, st);
     } else if constexpr (N == 32) {
         // measured (fraction of HBM peak): 4 lanes per matrix 0.47, 8 lanes 0.39, 16 lanes 0.31: fewer lanes per matrix
         // mean fewer shuffles per useful operation, even at half the warps per SM
-        return launch_rows<N, 4, VARIANT, 6>(A, L, batch, st);
+        return launch_rows<N, 4, VARIANT, 6, FUSED>(A, L, batch, st);
     } else if constexpr (N == 64) {
-        return launch_rows<N, 32, VARIANT, 12>(A, L, batch, st);  // 16 lanes per matrix measured slower (0.152 vs 0.168)
+        return launch_rows<N, 32, VARIANT, 12, FUSED>(A, L, batch, st);  // 16 lanes per matrix measured slower (0.152 vs 0.168)
     } else {
-        return launch_tpm_w<N, VARIANT, 8>(A, L, batch, st);
+        return launch_tpm_w<N, VARIANT, 8, FUSED>(A, L, batch, st);
     }
 }
 
@@ -499,7 +483,7 @@ static cudaError_t launch_group(const float* A, float* L, int n, long batch, cud
     const size_t per = ((size_t)n * (n | 1) + n) * 4;
     const size_t smem = per * kGroups;
     auto kern = chol_group_kernel<G, VARIANT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_dynamic_smem(kern, smem);
     if (e != cudaSuccess) return e;
     int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(227 * 1024) / (smem + 1024)));
     long grid = std::min<long>((batch + kGroups - 1) / kGroups, (long)sm_count() * ctas_per_sm);
@@ -508,19 +492,20 @@ static cudaError_t launch_group(const float* A, float* L, int n, long batch, cud
     return cudaGetLastError();
 }
 
-template <int VARIANT>
+template <int VARIANT, bool FUSED>
 static cudaError_t chol_dispatch(const float* A, float* L, int n, long batch, int path, cudaStream_t st) {
     const bool aligned = (((uintptr_t)A | (uintptr_t)L) & 15) == 0;
     // 128 x 128, right-looking designs: the register-tiled CTA-per-matrix kernel (blocked.cu, exact mode)
-    if (VARIANT == 0 && n == 128 && (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM)) return cholesky128_exact(A, L, batch, st);
+    if (VARIANT == 0 && n == 128 && (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM)) return cholesky128_exact(A, L, batch, FUSED, st);
     if (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM) {
-        if (aligned && n == 4) return launch_tpm<4, VARIANT>(A, L, batch, st);
-        if (aligned && n == 8) return launch_tpm<8, VARIANT>(A, L, batch, st);
-        if (aligned && n == 16) return launch_tpm<16, VARIANT>(A, L, batch, st);
-        if (aligned && n == 32) return launch_tpm<32, VARIANT>(A, L, batch, st);
-        if (aligned && n == 64) return launch_tpm<64, VARIANT>(A, L, batch, st);
+        if (aligned && n == 4) return launch_tpm<4, VARIANT, FUSED>(A, L, batch, st);
+        if (aligned && n == 8) return launch_tpm<8, VARIANT, FUSED>(A, L, batch, st);
+        if (aligned && n == 16) return launch_tpm<16, VARIANT, FUSED>(A, L, batch, st);
+        if (aligned && n == 32) return launch_tpm<32, VARIANT, FUSED>(A, L, batch, st);
+        if (aligned && n == 64) return launch_tpm<64, VARIANT, FUSED>(A, L, batch, st);
         if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
     }
+    // (the kernels below have no fused form: HLSD_FLAG_FUSED is a permission, not a request)
     const size_t per = ((size_t)n * (n | 1) + n) * 4;
     const size_t cap = 227 * 1024 - 1024;
     if ((path == HLSD_PATH_AUTO && per <= cap) || path == HLSD_PATH_GROUP) {
@@ -532,18 +517,20 @@ static cudaError_t chol_dispatch(const float* A, float* L, int n, long batch, in
     // global-memory fallback
     float* scratch = nullptr;
     long grid = std::min<long>(batch, (long)sm_count() * 2);
-    cudaError_t e = cudaMallocAsync(&scratch, sizeof(float) * (size_t)grid * n, st);
+    cudaError_t e = ws_alloc(reinterpret_cast<void**>(&scratch), sizeof(float) * (size_t)grid * n, st);
     if (e != cudaSuccess) return e;
     chol_global_kernel<VARIANT><<<(unsigned)grid, 1024, 0, st>>>(A, L, scratch, n, batch);
     count_launch();
     e = cudaGetLastError();
-    cudaFreeAsync(scratch, st);
+    ws_free(scratch, st);
     return e;
 }
 
-cudaError_t cholesky_exact(const float* A, float* L, int n, long batch, int variant, int path, cudaStream_t st) {
+cudaError_t cholesky_exact(const float* A, float* L, int n, long batch, int variant, int path, int fused, cudaStream_t st) {
     if (batch == 0) return cudaSuccess;
-    return variant == 1 ? chol_dispatch<1>(A, L, n, batch, path, st) : chol_dispatch<0>(A, L, n, batch, path, st);
+    if (fused)
+        return variant == 1 ? chol_dispatch<1, true>(A, L, n, batch, path, st) : chol_dispatch<0, true>(A, L, n, batch, path, st);
+    return variant == 1 ? chol_dispatch<1, false>(A, L, n, batch, path, st) : chol_dispatch<0, false>(A, L, n, batch, path, st);
 }
 
 }  // namespace hlsd

@@ -30,11 +30,16 @@ __device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b)
 __device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float xsqrt(float a) { return __fsqrt_rn(a); }
 // IEEE division of several numerators by one divisor.  The reciprocal and its Newton step are computed once;
-// each quotient then costs three operations: q0 = a*r, rem = a - b*q0 (exact, fused), q = q0 + rem*r.  This is
-// the sequence nvcc itself emits for `div.rn.f32` on its fast path (MUFU.RCP + 5 FFMA), where it is guarded
-// by a range check (FCHK) that sends zeros, subnormals, infinities, NaNs and extreme exponents to a slow
-// subroutine; here the guard is `in_range` (a conservative sub-range of the fast path's), and anything
-// outside falls back to __fdiv_rn.  Both give the correctly rounded quotient, so results do not change.
+// each quotient then costs three operations: q0 = a*r, rem = a - b*q0 (exact, fused), q = q0 + rem*r.  The
+// result is the correctly rounded quotient whenever the refined reciprocal r equals RN(1/b) (Markstein), which
+// the Newton step guarantees from any MUFU.RCP value within 2 ulp - EXCEPT for divisors whose mantissa is all
+// ones, where r can stay one ulp low and a power-of-two numerator then lands on a false tie
+// (0x1p23 / 0x1.fffffep23 -> 0x1p-1 instead of 0x1.000002p-1; round-1 advisor finding, reproduced on the CPU
+// with glibc fmaf: 65 694 mismatches in 96 M hard cases with those divisors, 0 in 154 M without them, and a
+// second residual correction does not help because the residual is exact and r is what is off).  Such
+// divisors, zeros, subnormals, infinities, NaNs and extreme exponents (`div_in_range`, a conservative
+// sub-range of what nvcc's own fast path accepts) fall back to __fdiv_rn.  tests/test_gpu_division.py checks
+// the quotients bit for bit against __fdiv_rn on the device, including all-ones and near-all-ones divisors.
 struct SharedDivisor {
     float b, r;
     bool ok;
@@ -47,7 +52,8 @@ __device__ __forceinline__ SharedDivisor make_divisor(float b) {
     float r0;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(b));
     const float e = __fmaf_rn(-b, r0, 1.0f);
-    return SharedDivisor{b, __fmaf_rn(r0, e, r0), div_in_range(b)};
+    const bool all_ones = (__float_as_uint(b) & 0x7fffffu) == 0x7fffffu;
+    return SharedDivisor{b, __fmaf_rn(r0, e, r0), div_in_range(b) && !all_ones};
 }
 __device__ __forceinline__ float fast_quotient(float a, const SharedDivisor& d) {
     const float q0 = __fmul_rn(a, d.r);
@@ -62,12 +68,30 @@ __device__ __forceinline__ float xdiv(float a, const SharedDivisor& d) {
 // a - b*c, two roundings
 __device__ __forceinline__ float xmsub(float a, float b, float c) { return __fsub_rn(a, __fmul_rn(b, c)); }
 
+// the same with the contraction HLSD_FLAG_FUSED allows (FUSED: one rounding)
+template <bool FUSED>
+__device__ __forceinline__ float msub(float a, float b, float c) {
+    if constexpr (FUSED) return __fmaf_rn(-b, c, a);
+    else return xmsub(a, b, c);
+}
+
 // qrf_mm of the reference (QR/qr_v2.1/model4x4/qr.cpp:52-60): a' = op2*s + op1*c ; b' = op2*c - op1*s
 __device__ __forceinline__ void givens_apply(float c, float s, float& op1, float& op2) {
     float a = xadd(xmul(op2, s), xmul(op1, c));
     float b = xsub(xmul(op2, c), xmul(op1, s));
     op1 = a;
     op2 = b;
+}
+template <bool FUSED>
+__device__ __forceinline__ void givens_apply_t(float c, float s, float& op1, float& op2) {
+    if constexpr (FUSED) {
+        const float a = __fmaf_rn(op2, s, __fmul_rn(op1, c));
+        const float b = __fmaf_rn(op2, c, -__fmul_rn(op1, s));
+        op1 = a;
+        op2 = b;
+    } else {
+        givens_apply(c, s, op1, op2);
+    }
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -9,13 +9,24 @@ namespace hlsd {
 
 void count_launch();  // bumps the process-wide launch counter reported by hlsd_launch_count()
 int sm_count();
+// cudaFuncAttributeMaxDynamicSharedMemorySize, issued once per (kernel, device) - again only if a later call needs
+// more - and checked
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes);
+template <class K>
+inline cudaError_t ensure_dynamic_smem(K* kernel, size_t bytes) {
+    return ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), bytes);
+}
+// stream-ordered workspace memory from a library-owned pool (the device's default pool is left alone)
+cudaError_t ws_alloc(void** p, size_t bytes, cudaStream_t st);
+void ws_free(void* p, cudaStream_t st);
 
 // Exact paths: every float operation of the reference design, in its per-element order, rounded
 // separately.  `path` is one of HLSD_PATH_* (AUTO picks by size).  All enqueue on `st`.
-cudaError_t cholesky_exact(const float* A, float* L, int n, long batch, int variant, int path, cudaStream_t st);
-cudaError_t lu_exact(const float* A, float* L, float* U, int* P, int n, long batch, int pivoting, int path,
+// `fused` != 0 (HLSD_FLAG_FUSED): kernels that have a fused form contract a - b*c / the Givens pair into FMAs.
+cudaError_t cholesky_exact(const float* A, float* L, int n, long batch, int variant, int path, int fused, cudaStream_t st);
+cudaError_t lu_exact(const float* A, float* L, float* U, int* P, int n, long batch, int pivoting, int path, int fused,
                      cudaStream_t st);
-cudaError_t qr_exact(const float* A, float* Q, float* R, int rows, int cols, long batch, int variant, int path,
+cudaError_t qr_exact(const float* A, float* Q, float* R, int rows, int cols, long batch, int variant, int path, int fused,
                      cudaStream_t st);
 
 // Blocked right-looking Cholesky for large N (n % 64 == 0, n >= 128): SIMT panel factorisation +
@@ -24,13 +35,14 @@ cudaError_t qr_exact(const float* A, float* Q, float* R, int rows, int cols, lon
 cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int use_tensor, cudaStream_t st);
 
 // Bit-identical Cholesky (right-looking designs) of 128 x 128 matrices, register-tiled, one CTA per matrix.
-cudaError_t cholesky128_exact(const float* A, float* L, long batch, cudaStream_t st);
+cudaError_t cholesky128_exact(const float* A, float* L, long batch, int fused, cudaStream_t st);
 
 // Blocked LU with partial pivoting, tensor-core trailing update (n % 128 == 0, 256 <= n <= 1024).
 cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long batch, cudaStream_t st);
 
 // Self-check: shared-divisor division (common.cuh) vs IEEE division over `count` device-resident pairs;
-// out2[0] = bitwise mismatches, out2[1] = pairs served by the fast path (device memory, 2 x int64).
+// out[0] = bitwise mismatches, out[1] = pairs served by the fast path, out[2] = mismatches of the unguarded
+// sequence (device memory, 3 x int64).
 cudaError_t selftest_division(const float* num, const float* den, long count, long long* out2, cudaStream_t st);
 
 }  // namespace hlsd

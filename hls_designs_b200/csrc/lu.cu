@@ -10,8 +10,6 @@
 //   lu_lane_kernel<N>     one lane per row, N = 64 (two warps per matrix).
 //   lu_group_kernel<G>    G threads per matrix, matrix resident in shared memory.
 //   lu_global_kernel      one CTA per matrix, in place in global memory (any N; exact; slow).
-#include <cstdlib>
-
 #include "common.cuh"
 #include "kernels.h"
 
@@ -36,7 +34,7 @@ __device__ __forceinline__ float pivot_key(float x, bool is_diag) {
 // ------------------------------------------------------------------------------------------------
 // thread-per-matrix (registers), slabs staged by bulk copies as in chol_tpm_kernel
 // ------------------------------------------------------------------------------------------------
-template <int N, int WARPS>
+template <int N, int WARPS, bool FUSED>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 lu_tpm_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restrict__ U, int* __restrict__ P,
               long batch, int pivoting) {
@@ -118,7 +116,7 @@ lu_tpm_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restr
 #pragma unroll
                 for (int i = k + 1; i < N; i++)
 #pragma unroll
-                    for (int j = k + 1; j < N; j++) a[i][j] = xmsub(a[i][j], a[i][k], a[k][j]);
+                    for (int j = k + 1; j < N; j++) a[i][j] = msub<FUSED>(a[i][j], a[i][k], a[k][j]);
             }
             piv[N - 1] = N - 1;
             float4* l4 = reinterpret_cast<float4*>(slotA);
@@ -173,7 +171,7 @@ lu_tpm_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restr
 // bit-identical.  Rows that have already served as pivot rows are dead data and are updated along with
 // the live ones (no predication); only their L stores are masked.
 // ------------------------------------------------------------------------------------------------
-template <int N, int R, int WARPS, bool PIVOT, bool U_DIRECT>
+template <int N, int R, int WARPS, bool PIVOT, bool U_DIRECT, bool FUSED>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restrict__ U, int* __restrict__ P,
                long batch) {
@@ -310,13 +308,13 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
                 // column k+1 first: the next step's pivot search only needs that one and its shuffles
                 // overlap the rest of the update (one straight-line block, the scheduler interleaves)
 #pragma unroll
-                for (int t = 0; t < T; t++) a[t][k + 1] = xmsub(a[t][k + 1], lm[t], u[k + 1]);
+                for (int t = 0; t < T; t++) a[t][k + 1] = msub<FUSED>(a[t][k + 1], lm[t], u[k + 1]);
                 p = search(std::integral_constant<int, k + 1>{});
 #pragma unroll
                 for (int t = 0; t < T; t++) {
                     if (pos[t] > k) sA[pos[t] * N + k] = lm[t];
 #pragma unroll
-                    for (int j = k + 2; j < N; j++) a[t][j] = xmsub(a[t][j], lm[t], u[j]);
+                    for (int j = k + 2; j < N; j++) a[t][j] = msub<FUSED>(a[t][j], lm[t], u[j]);
                 }
             }
         });
@@ -341,7 +339,7 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
 // barriers per column (after the partials, after the pivot row); the butterfly of the next column's
 // search is issued right after that column is updated and overlaps the rest of the update.
 // ------------------------------------------------------------------------------------------------
-template <int N, int MATS, bool PIVOT>
+template <int N, int MATS, bool PIVOT, bool FUSED>
 __global__ void __launch_bounds__(MATS * N, 1)
 lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restrict__ U, int* __restrict__ P,
                long batch) {
@@ -451,19 +449,19 @@ lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
                 constexpr int q1 = (k + 1) / 4;  // the quad of column k+1 first: the next search only needs that column
                 {
                     const float4 u = ur4[q1];
-                    if (4 * q1 > k) a[4 * q1] = xmsub(a[4 * q1], lm, u.x);
-                    if (4 * q1 + 1 > k) a[4 * q1 + 1] = xmsub(a[4 * q1 + 1], lm, u.y);
-                    if (4 * q1 + 2 > k) a[4 * q1 + 2] = xmsub(a[4 * q1 + 2], lm, u.z);
-                    a[4 * q1 + 3] = xmsub(a[4 * q1 + 3], lm, u.w);
+                    if (4 * q1 > k) a[4 * q1] = msub<FUSED>(a[4 * q1], lm, u.x);
+                    if (4 * q1 + 1 > k) a[4 * q1 + 1] = msub<FUSED>(a[4 * q1 + 1], lm, u.y);
+                    if (4 * q1 + 2 > k) a[4 * q1 + 2] = msub<FUSED>(a[4 * q1 + 2], lm, u.z);
+                    a[4 * q1 + 3] = msub<FUSED>(a[4 * q1 + 3], lm, u.w);
                 }
                 cand = search(std::integral_constant<int, k + 1>{});
 #pragma unroll
                 for (int q = q1 + 1; q < N / 4; q++) {
                     const float4 u = ur4[q];
-                    a[4 * q] = xmsub(a[4 * q], lm, u.x);
-                    a[4 * q + 1] = xmsub(a[4 * q + 1], lm, u.y);
-                    a[4 * q + 2] = xmsub(a[4 * q + 2], lm, u.z);
-                    a[4 * q + 3] = xmsub(a[4 * q + 3], lm, u.w);
+                    a[4 * q] = msub<FUSED>(a[4 * q], lm, u.x);
+                    a[4 * q + 1] = msub<FUSED>(a[4 * q + 1], lm, u.y);
+                    a[4 * q + 2] = msub<FUSED>(a[4 * q + 2], lm, u.z);
+                    a[4 * q + 3] = msub<FUSED>(a[4 * q + 3], lm, u.w);
                 }
             }
         });
@@ -587,13 +585,13 @@ lu_global_kernel(const float* __restrict__ A, float* __restrict__ L, float* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int N>
+template <int N, bool FUSED>
 static cudaError_t launch_lu_tpm(const float* A, float* L, float* U, int* P, long batch, int pivoting, cudaStream_t st) {
     constexpr int WARPS = 8;
     constexpr int kSlot = N * N + 4;
     const size_t smem = (size_t)WARPS * 2 * 32 * kSlot * 4 + WARPS * sizeof(uint64_t);
-    auto kern = lu_tpm_kernel<N, WARPS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = lu_tpm_kernel<N, WARPS, FUSED>;
+    cudaError_t e = ensure_dynamic_smem(kern, smem);
     if (e != cudaSuccess) return e;
     const long num_slabs = (batch + 31) / 32;
     int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024) / (smem + 1024)));
@@ -603,7 +601,7 @@ static cudaError_t launch_lu_tpm(const float* A, float* L, float* U, int* P, lon
     return cudaGetLastError();
 }
 
-template <int N, int R, int WARPS, bool U_DIRECT = false>
+template <int N, int R, int WARPS, bool FUSED, bool U_DIRECT = false>
 static cudaError_t launch_lu_regs(const float* A, float* L, float* U, int* P, long batch, int pivoting, cudaStream_t st) {
     constexpr int MPW = 32 / R;
     constexpr size_t per_warp = (size_t)MPW * ((U_DIRECT ? 1 : 2) * (N * N + 4) + N) * 4;
@@ -611,8 +609,8 @@ static cudaError_t launch_lu_regs(const float* A, float* L, float* U, int* P, lo
     const size_t smem = WARPS * per_warp + WARPS * sizeof(uint64_t);
     // (one bulk copy per matrix: measured 7-13 % faster here than one part per lane, the opposite of the
     // HBM-bound Cholesky kernels, which prefer many small copies in flight)
-    auto kern = pivoting ? lu_regs_kernel<N, R, WARPS, true, U_DIRECT> : lu_regs_kernel<N, R, WARPS, false, U_DIRECT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = pivoting ? lu_regs_kernel<N, R, WARPS, true, U_DIRECT, FUSED> : lu_regs_kernel<N, R, WARPS, false, U_DIRECT, FUSED>;
+    cudaError_t e = ensure_dynamic_smem(kern, smem);
     if (e != cudaSuccess) return e;
     const long num_slabs = (batch + MPW - 1) / MPW;
     long grid = std::min<long>((num_slabs + WARPS - 1) / WARPS, (long)sm_count());
@@ -621,7 +619,7 @@ static cudaError_t launch_lu_regs(const float* A, float* L, float* U, int* P, lo
     return cudaGetLastError();
 }
 
-template <int N>
+template <int N, bool FUSED>
 static cudaError_t launch_lu_lane(const float* A, float* L, float* U, int* P, long batch, int pivoting, cudaStream_t st) {
     constexpr size_t per_mat = (size_t)((N * N + 4) + 2 * N + N + 8) * 4;
     constexpr int fit = (int)((227 * 1024 - 1024) / (per_mat + 8));
@@ -630,8 +628,8 @@ static cudaError_t launch_lu_lane(const float* A, float* L, float* U, int* P, lo
     constexpr int by_regs = 65536 / ((N + 38) * N);
     constexpr int MATS = fit * N > 1024 ? 1024 / N : (fit < by_regs ? fit : by_regs);
     const size_t smem = MATS * per_mat + MATS * sizeof(uint64_t);
-    auto kern = pivoting ? lu_lane_kernel<N, MATS, true> : lu_lane_kernel<N, MATS, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = pivoting ? lu_lane_kernel<N, MATS, true, FUSED> : lu_lane_kernel<N, MATS, false, FUSED>;
+    cudaError_t e = ensure_dynamic_smem(kern, smem);
     if (e != cudaSuccess) return e;
     long grid = std::min<long>((batch + MATS - 1) / MATS, (long)sm_count());
     kern<<<(unsigned)grid, MATS * N, smem, st>>>(A, L, U, P, batch);
@@ -645,7 +643,7 @@ static cudaError_t launch_lu_group(const float* A, float* L, float* U, int* P, i
     constexpr int kGroups = 256 / G;
     const size_t smem = (size_t)n * (n | 1) * 4 * kGroups;
     auto kern = lu_group_kernel<G>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_dynamic_smem(kern, smem);
     if (e != cudaSuccess) return e;
     int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(227 * 1024) / (smem + 1024)));
     long grid = std::min<long>((batch + kGroups - 1) / kGroups, (long)sm_count() * ctas_per_sm);
@@ -654,16 +652,16 @@ static cudaError_t launch_lu_group(const float* A, float* L, float* U, int* P, i
     return cudaGetLastError();
 }
 
-cudaError_t lu_exact(const float* A, float* L, float* U, int* P, int n, long batch, int pivoting, int path,
-                     cudaStream_t st) {
-    if (batch == 0) return cudaSuccess;
+template <bool FUSED>
+static cudaError_t lu_dispatch(const float* A, float* L, float* U, int* P, int n, long batch, int pivoting, int path,
+                               cudaStream_t st) {
     const bool aligned = (((uintptr_t)A | (uintptr_t)L | (uintptr_t)U | (uintptr_t)P) & 15) == 0;
     if (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM) {
-        if (aligned && n == 4) return launch_lu_tpm<4>(A, L, U, P, batch, pivoting, st);
-        if (aligned && n == 8) return launch_lu_regs<8, 2, 20>(A, L, U, P, batch, pivoting, st);
-        if (aligned && n == 16) return launch_lu_regs<16, 4, 12, true>(A, L, U, P, batch, pivoting, st);  // U rows straight out: +10 %
-        if (aligned && n == 32) return launch_lu_regs<32, 16, 10>(A, L, U, P, batch, pivoting, st);  // (lane kernel: 97 M vs 121 M fact/s)
-        if (aligned && n == 64) return launch_lu_lane<64>(A, L, U, P, batch, pivoting, st);
+        if (aligned && n == 4) return launch_lu_tpm<4, FUSED>(A, L, U, P, batch, pivoting, st);
+        if (aligned && n == 8) return launch_lu_regs<8, 2, 20, FUSED>(A, L, U, P, batch, pivoting, st);
+        if (aligned && n == 16) return launch_lu_regs<16, 4, 12, FUSED, true>(A, L, U, P, batch, pivoting, st);  // U rows straight out: +10 %
+        if (aligned && n == 32) return launch_lu_regs<32, 16, 10, FUSED>(A, L, U, P, batch, pivoting, st);  // (lane kernel: 97 M vs 121 M fact/s)
+        if (aligned && n == 64) return launch_lu_lane<64, FUSED>(A, L, U, P, batch, pivoting, st);
         if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
     }
     const size_t per = (size_t)n * (n | 1) * 4;
@@ -678,6 +676,13 @@ cudaError_t lu_exact(const float* A, float* L, float* U, int* P, int n, long bat
     lu_global_kernel<<<(unsigned)grid, 1024, 0, st>>>(A, L, U, P, n, batch, pivoting);
     count_launch();
     return cudaGetLastError();
+}
+
+cudaError_t lu_exact(const float* A, float* L, float* U, int* P, int n, long batch, int pivoting, int path, int fused,
+                     cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    return fused ? lu_dispatch<true>(A, L, U, P, n, batch, pivoting, path, st)
+                 : lu_dispatch<false>(A, L, U, P, n, batch, pivoting, path, st);
 }
 
 }  // namespace hlsd

@@ -23,8 +23,6 @@
 //   qr_wave_kernel<G>    G threads per matrix, R and Q resident in shared memory, wavefront schedule
 //                        (variant 0) or sequential schedule (variant 1).
 //   qr_global_kernel     one CTA per matrix, in place in global memory (any size; exact; slow).
-#include <cstdlib>
-
 #include "common.cuh"
 #include "kernels.h"
 
@@ -50,10 +48,16 @@ __device__ __forceinline__ bool givens_skip(float hi) {
 }
 // qr_v2.1 angle generation with one reciprocal for the two divisions (make_divisor / fast_quotient, common.cuh);
 // a skipped rotation (hi == 0) computes on (1, 1) so that it stays on the fast paths, and is then discarded
+template <bool FUSED>
+__device__ __forceinline__ float givens_mag(float x, float y) {
+    if constexpr (FUSED) return xsqrt(__fmaf_rn(x, x, xmul(y, y)));
+    else return xsqrt(xadd(xmul(x, x), xmul(y, y)));
+}
+template <bool FUSED = false>
 __device__ __forceinline__ void givens_make_fast(float& lo, float& hi, float& c, float& s) {
     const bool skip = givens_skip<0>(hi);
     const float x = skip ? 1.0f : hi, y = skip ? 1.0f : lo;
-    const float mag = xsqrt(xadd(xmul(x, x), xmul(y, y)));
+    const float mag = givens_mag<FUSED>(x, y);
     const SharedDivisor dv = make_divisor(mag);
     float cq, sq;
     if (dv.ok && div_in_range(x) && div_in_range(y)) {
@@ -72,7 +76,7 @@ __device__ __forceinline__ void givens_make_fast(float& lo, float& hi, float& c,
 // ------------------------------------------------------------------------------------------------
 // thread-per-matrix (registers): square N x N
 // ------------------------------------------------------------------------------------------------
-template <int N, int VARIANT, int WARPS>
+template <int N, int VARIANT, int WARPS, bool FUSED>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 qr_tpm_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restrict__ R, long batch) {
     constexpr int kSlot = N * N + 4;
@@ -127,15 +131,13 @@ qr_tpm_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restr
             for (int col = 0; col < N; col++) {
 #pragma unroll
                 for (int i = N - 1; i > col; i--) {
-                    constexpr int dummy = 0;
-                    (void)dummy;
                     const int lo = (VARIANT == 0) ? i - 1 : ((col == 0 && i < 2) ? i - 1 : i - 2);
                     float c, s;
                     givens_make(r[lo][col], r[i][col], givens_skip<VARIANT>(r[i][col]), c, s);
 #pragma unroll
-                    for (int j = col + 1; j < N; j++) givens_apply(c, s, r[lo][j], r[i][j]);
+                    for (int j = col + 1; j < N; j++) givens_apply_t<FUSED>(c, s, r[lo][j], r[i][j]);
 #pragma unroll
-                    for (int k = 0; k < N; k++) givens_apply(c, s, q[k][lo], q[k][i]);
+                    for (int k = 0; k < N; k++) givens_apply_t<FUSED>(c, s, q[k][lo], q[k][i]);
                 }
             }
             float4* r4 = reinterpret_cast<float4*>(slotR);
@@ -262,7 +264,7 @@ qr_cols_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
 // (c, s) is broadcast by shuffle and applied by all lanes of the group to their columns of R to the right
 // of c and to their rows of Q.  Per-element operation order is the sequential loop's: bit-identical.
 // ------------------------------------------------------------------------------------------------
-template <int N, int K, int WARPS>
+template <int N, int K, int WARPS, bool FUSED>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 qr_wcols_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restrict__ R, long batch) {
     constexpr int C = N / K;     // lanes per matrix
@@ -324,7 +326,7 @@ qr_wcols_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __res
                     // angle generation, all owners at once; a skipped rotation (hi == 0) computes on (1, 1)
                     const bool skip = givens_skip<0>(hi);
                     const float x = skip ? 1.0f : hi, y = skip ? 1.0f : lo;
-                    const float mag = xsqrt(xadd(xmul(x, x), xmul(y, y)));
+                    const float mag = givens_mag<FUSED>(x, y);
                     const SharedDivisor dv = make_divisor(mag);
                     float cs, sn;
                     if (dv.ok && div_in_range(x) && div_in_range(y)) {
@@ -347,17 +349,17 @@ qr_wcols_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __res
                         {
                             const float a0 = rr[kc][i - 1], b0 = rr[kc][i];
                             float a1 = a0, b1 = b0;
-                            givens_apply(cc, ss, a1, b1);
+                            givens_apply_t<FUSED>(cc, ss, a1, b1);
                             rr[kc][i - 1] = (l == lc) ? new_lo : (l > lc ? a1 : a0);
                             rr[kc][i] = (l == lc) ? new_hi : (l > lc ? b1 : b0);
                         }
                         static_for<kc + 1, K>([&](auto kkc) {
                             constexpr int kk = decltype(kkc)::value;
-                            givens_apply(cc, ss, rr[kk][i - 1], rr[kk][i]);
+                            givens_apply_t<FUSED>(cc, ss, rr[kk][i - 1], rr[kk][i]);
                         });
                         static_for<0, K>([&](auto kkc) {
                             constexpr int kk = decltype(kkc)::value;
-                            givens_apply(cc, ss, qq[kk][i - 1], qq[kk][i]);
+                            givens_apply_t<FUSED>(cc, ss, qq[kk][i - 1], qq[kk][i]);
                         });
                     });
                 });
@@ -519,7 +521,7 @@ qr_wave_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
 // offset from a per-step base pointer.  Per rotation and Q row: one 8-byte shared-memory load and the six
 // floating-point operations, instead of two loads, two stores and address arithmetic on top.
 // ------------------------------------------------------------------------------------------------
-template <int N, int RT>
+template <int N, int RT, bool FUSED>
 __global__ void __launch_bounds__(RT + N, N == 64 ? 4 : 1)
 qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restrict__ R, long batch) {
     extern __shared__ __align__(16) float smem_f[];
@@ -549,7 +551,7 @@ qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
                     const int c = c_lo + k, i = i0 + 2 * k;
                     float lo = r[(i - 1) * ldr + c], hi = r[i * ldr + c];
                     float cc, ss;
-                    givens_make_fast(lo, hi, cc, ss);
+                    givens_make_fast<FUSED>(lo, hi, cc, ss);
                     r[(i - 1) * ldr + c] = lo;
                     r[i * ldr + c] = hi;
                     cs2[k] = make_float2(cc, ss);
@@ -587,7 +589,7 @@ qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
                         const int kmax = min(nrot, tx + 32 * xc - c_lo);
 #pragma unroll
                         for (int j = 0; j < 4; j++)
-                            if (k + j * GY < kmax) givens_apply(w[j].x, w[j].y, lo[xc][j], hi[xc][j]);
+                            if (k + j * GY < kmax) givens_apply_t<FUSED>(w[j].x, w[j].y, lo[xc][j], hi[xc][j]);
                     }
 #pragma unroll
                     for (int xc = 0; xc < XC; xc++) {
@@ -618,7 +620,7 @@ qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
                                 constexpr int lo = 2 * p + PAR - 1, hi = 2 * p + PAR;
                                 if constexpr (lo >= 0) {
                                     const float2 w = csp[p];
-                                    givens_apply(w.x, w.y, qq[lo], qq[hi]);
+                                    givens_apply_t<FUSED>(w.x, w.y, qq[lo], qq[hi]);
                                 }
                             });
                         } else if (8 * g + 7 >= plo && 8 * g <= phi) {
@@ -630,7 +632,7 @@ qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
                                     const bool on = p >= plo && p <= phi;
                                     const float2 w = csp[p];
                                     float x0 = qq[lo], x1 = qq[hi];
-                                    givens_apply(w.x, w.y, x0, x1);
+                                    givens_apply_t<FUSED>(w.x, w.y, x0, x1);
                                     qq[lo] = on ? x0 : qq[lo];
                                     qq[hi] = on ? x1 : qq[hi];
                                 }
@@ -678,13 +680,13 @@ qr_global_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int N, int VARIANT>
+template <int N, int VARIANT, bool FUSED>
 static cudaError_t launch_qr_tpm(const float* A, float* Q, float* R, long batch, cudaStream_t st) {
     constexpr int WARPS = (N == 8) ? 4 : 8;
     constexpr int kSlot = N * N + 4;
     const size_t smem = (size_t)WARPS * 2 * 32 * kSlot * 4 + WARPS * sizeof(uint64_t);
-    auto kern = qr_tpm_kernel<N, VARIANT, WARPS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = qr_tpm_kernel<N, VARIANT, WARPS, FUSED>;
+    cudaError_t e = ensure_dynamic_smem(kern, smem);
     if (e != cudaSuccess) return e;
     const long num_slabs = (batch + 31) / 32;
     int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(227 * 1024) / (smem + 1024)));
@@ -700,7 +702,7 @@ static cudaError_t launch_qr_cols(const float* A, float* Q, float* R, long batch
     constexpr int WARPS = (N == 16) ? 16 : 12;
     const size_t smem = (size_t)WARPS * MPW * 2 * (N * N + 4) * 4 + WARPS * sizeof(uint64_t);
     auto kern = qr_cols_kernel<N, VARIANT, WARPS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_dynamic_smem(kern, smem);
     if (e != cudaSuccess) return e;
     const long num_slabs = (batch + MPW - 1) / MPW;
     int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (size_t)(227 * 1024) / (smem + 1024)));
@@ -710,12 +712,12 @@ static cudaError_t launch_qr_cols(const float* A, float* Q, float* R, long batch
     return cudaGetLastError();
 }
 
-template <int N, int K, int WARPS>
+template <int N, int K, int WARPS, bool FUSED>
 static cudaError_t launch_qr_wcols(const float* A, float* Q, float* R, long batch, cudaStream_t st) {
     constexpr int MPW = 32 / (N / K);
     const size_t smem = (size_t)WARPS * MPW * 2 * (N * N + 4) * 4 + WARPS * sizeof(uint64_t);
-    auto kern = qr_wcols_kernel<N, K, WARPS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = qr_wcols_kernel<N, K, WARPS, FUSED>;
+    cudaError_t e = ensure_dynamic_smem(kern, smem);
     if (e != cudaSuccess) return e;
     const long num_slabs = (batch + MPW - 1) / MPW;
     long grid = std::min<long>((num_slabs + WARPS - 1) / WARPS, (long)sm_count());
@@ -724,21 +726,11 @@ static cudaError_t launch_qr_wcols(const float* A, float* Q, float* R, long batc
     return cudaGetLastError();
 }
 
-// HLSD_QR_REGS=1 (environment): the older kernels for 8x8 / 16x16 / 32x32 (A/B measurements)
-static int qr_regs_mode() {
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("HLSD_QR_REGS");
-        mode = e ? atoi(e) : 0;
-    }
-    return mode;
-}
-
-template <int N, int RT>
+template <int N, int RT, bool FUSED>
 static cudaError_t launch_qr_qreg(const float* A, float* Q, float* R, long batch, cudaStream_t st) {
     const size_t smem = ((size_t)N * (N | 1) + 2 * (N / 2 + 2 + 8 + 4 * (RT / 32))) * 4;  // slack behind cs: 3 * GY entries
-    auto kern = qr_qreg_kernel<N, RT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = qr_qreg_kernel<N, RT, FUSED>;
+    cudaError_t e = ensure_dynamic_smem(kern, smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RT + N, smem);
@@ -758,7 +750,7 @@ static cudaError_t launch_qr_wave(const float* A, float* Q, float* R, int rows, 
     constexpr int kGroups = kBlock / G;
     const size_t smem = qr_smem_per_matrix(rows, cols) * kGroups;
     auto kern = qr_wave_kernel<G, VARIANT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_dynamic_smem(kern, smem);
     if (e != cudaSuccess) return e;
     int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(227 * 1024) / (smem + 1024)));
     long grid = std::min<long>((batch + kGroups - 1) / kGroups, (long)sm_count() * ctas_per_sm);
@@ -767,34 +759,34 @@ static cudaError_t launch_qr_wave(const float* A, float* Q, float* R, int rows, 
     return cudaGetLastError();
 }
 
-template <int VARIANT>
+template <int VARIANT, bool FUSED>
 static cudaError_t qr_dispatch(const float* A, float* Q, float* R, int rows, int cols, long batch, int path,
                                cudaStream_t st) {
     const bool aligned = (((uintptr_t)A | (uintptr_t)Q | (uintptr_t)R) & 15) == 0;
     if (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM) {
-        if (aligned && rows == 4 && cols == 4) return launch_qr_tpm<4, VARIANT>(A, Q, R, batch, st);
+        if (aligned && rows == 4 && cols == 4) return launch_qr_tpm<4, VARIANT, FUSED>(A, Q, R, batch, st);
         if (aligned && rows == 8 && cols == 8) {
             // two lanes per matrix, wavefront: 3.68 G fact/s against 2.95 G for one thread per matrix (batch 4M)
-            if (VARIANT == 0 && qr_regs_mode() == 0) return launch_qr_wcols<8, 4, 16>(A, Q, R, batch, st);
-            return launch_qr_tpm<8, VARIANT>(A, Q, R, batch, st);
+            if constexpr (VARIANT == 0) return launch_qr_wcols<8, 4, 16, FUSED>(A, Q, R, batch, st);
+            else return launch_qr_tpm<8, VARIANT, false>(A, Q, R, batch, st);
         }
         // measured (fact/s, batch 1M / 256k): 16x16 K = 1 / 2 / 4 columns per lane 325 M / 463 M / 390 M against 157 M for the
         // sequential lane-per-column kernel; 32x32 K = 1 / 2 39 M / 42 M against 29 M for the shared-memory wavefront
         if (aligned && rows == 16 && cols == 16) {
-            if (VARIANT == 0 && qr_regs_mode() == 0) return launch_qr_wcols<16, 2, 16>(A, Q, R, batch, st);
-            return launch_qr_cols<16, VARIANT>(A, Q, R, batch, st);
+            if constexpr (VARIANT == 0) return launch_qr_wcols<16, 2, 16, FUSED>(A, Q, R, batch, st);
+            else return launch_qr_cols<16, VARIANT>(A, Q, R, batch, st);
         }
         if (aligned && rows == 32 && cols == 32) {
-            if (VARIANT == 0 && qr_regs_mode() == 0) return launch_qr_wcols<32, 2, 12>(A, Q, R, batch, st);
-            if (path == HLSD_PATH_TPM) return launch_qr_cols<32, VARIANT>(A, Q, R, batch, st);
+            if constexpr (VARIANT == 0) return launch_qr_wcols<32, 2, 12, FUSED>(A, Q, R, batch, st);
+            else if (path == HLSD_PATH_TPM) return launch_qr_cols<32, VARIANT>(A, Q, R, batch, st);
         }
         if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
     }
-    if (VARIANT == 0 && aligned && rows == cols && path == HLSD_PATH_AUTO && qr_regs_mode() == 0) {
-        if (rows == 64) return launch_qr_qreg<64, 64>(A, Q, R, batch, st);  // (128 R threads, 3 CTAs per SM: 4.0 M vs 5.2 M fact/s)
+    if (VARIANT == 0 && aligned && rows == cols && path == HLSD_PATH_AUTO) {
+        if (rows == 64) return launch_qr_qreg<64, 64, FUSED>(A, Q, R, batch, st);  // (128 R threads, 3 CTAs per SM: 4.0 M vs 5.2 M fact/s)
         // (256 R threads would halve the R side of a step, but 384 threads cap the kernel at 168 registers and the
         // 128-register Q rows spill: 217 k instead of 545 k fact/s)
-        if (rows == 128) return launch_qr_qreg<128, 128>(A, Q, R, batch, st);
+        if (rows == 128) return launch_qr_qreg<128, 128, FUSED>(A, Q, R, batch, st);
     }
     const size_t per = qr_smem_per_matrix(rows, cols);
     const size_t cap = 227 * 1024 - 1024;
@@ -812,11 +804,12 @@ static cudaError_t qr_dispatch(const float* A, float* Q, float* R, int rows, int
     return cudaGetLastError();
 }
 
-cudaError_t qr_exact(const float* A, float* Q, float* R, int rows, int cols, long batch, int variant, int path,
+cudaError_t qr_exact(const float* A, float* Q, float* R, int rows, int cols, long batch, int variant, int path, int fused,
                      cudaStream_t st) {
     if (batch == 0) return cudaSuccess;
-    return variant == 1 ? qr_dispatch<1>(A, Q, R, rows, cols, batch, path, st)
-                        : qr_dispatch<0>(A, Q, R, rows, cols, batch, path, st);
+    if (variant == 1) return qr_dispatch<1, false>(A, Q, R, rows, cols, batch, path, st);  // qr_v1.x: exact only
+    return fused ? qr_dispatch<0, true>(A, Q, R, rows, cols, batch, path, st)
+                 : qr_dispatch<0, false>(A, Q, R, rows, cols, batch, path, st);
 }
 
 }  // namespace hlsd

@@ -15,6 +15,6 @@
 #endif
 typedef float matrix_t;
 static inline int top(matrix_t A[matrix_size][matrix_size], matrix_t L[matrix_size][matrix_size]) {
-    return hlsd_cholesky_host(&A[0][0], &L[0][0], matrix_size, 1, HLSD_CHOL_DESIGN, HLSD_PATH_AUTO);
+    return hlsd_cholesky_host(&A[0][0], &L[0][0], matrix_size, 1, HLSD_CHOL_DESIGN, HLSD_PATH_AUTO | HLSD_FLAG_EXACT);  // the csim's bits at every size
 }
 #endif

@@ -16,6 +16,6 @@ typedef float matrix_t;
 typedef uint32_t uint_i;
 static inline int top(matrix_t A[matrix_size][matrix_size], matrix_t L[matrix_size][matrix_size],
                       matrix_t U[matrix_size][matrix_size], uint_i P[matrix_size]) {
-    return hlsd_lu_host(&A[0][0], &L[0][0], &U[0][0], (int32_t*)P, matrix_size, 1, HLSD_LU_DESIGN, HLSD_PATH_AUTO);
+    return hlsd_lu_host(&A[0][0], &L[0][0], &U[0][0], (int32_t*)P, matrix_size, 1, HLSD_LU_DESIGN, HLSD_PATH_AUTO | HLSD_FLAG_EXACT);  // the csim's bits at every size
 }
 #endif

@@ -12,6 +12,6 @@
 #endif
 typedef float MATRIX_T;
 static inline int top(MATRIX_T A[ROWS][COLS], MATRIX_T Q[ROWS][ROWS], MATRIX_T R[ROWS][COLS]) {
-    return hlsd_qr_host(&A[0][0], &Q[0][0], &R[0][0], ROWS, COLS, 1, HLSD_QR_DESIGN, HLSD_PATH_AUTO);
+    return hlsd_qr_host(&A[0][0], &Q[0][0], &R[0][0], ROWS, COLS, 1, HLSD_QR_DESIGN, HLSD_PATH_AUTO | HLSD_FLAG_EXACT);  // the csim's bits at every size
 }
 #endif

@@ -70,9 +70,27 @@ typedef enum {
 #define HLSD_PATH_GLOBAL 3  /* one CTA per matrix in global memory: any N, exact, slow                */
 #define HLSD_PATH_BLOCKED 4 /* reserved (blocked with an exact-order SIMT trailing update): not built,
                                returns HLSD_ERR_UNSUPPORTED                                            */
-#define HLSD_PATH_TENSOR 5  /* blocked right-looking, tcgen05 tensor-core trailing update:
-                               Cholesky n >= 256, n % 128 == 0; LU 256 <= n <= 1024, n % 128 == 0     */
+#define HLSD_PATH_TENSOR 5  /* blocked, tcgen05 tensor-core trailing update (3xTF32, fp32 accumulate):
+                               Cholesky n >= 256, n % 128 == 0; LU 256 <= n <= 1024, n % 128 == 0;
+                               16-byte aligned buffers.  NOT bit-identical to the csim: element-wise
+                               agreement 1e-5 * max|L| (Cholesky) / 1e-3 * max|U| (LU, same pivots
+                               unless two candidates tie to round-off), residuals < 2e-6 / 5e-5      */
 #define HLSD_PATH_MASK 0xff
+/* HLSD_PATH_AUTO picks the fastest kernel that serves the request: the register/shared-memory exact
+ * kernels for n <= ~230, and for the right-looking Cholesky designs / the pivoted LU designs at the
+ * sizes and alignment listed under HLSD_PATH_TENSOR the tensor path (so AUTO at n = 256, 512, 1024 is
+ * tolerance-exact, and an unaligned pointer or n = 255 stays bit-exact).  Callers that need the csim's
+ * bits at every size set HLSD_FLAG_EXACT; the drop-in top() headers (hls_designs_b200/host/) do. */
+#define HLSD_FLAG_EXACT 0x100 /* never leave the reference design's arithmetic: AUTO does not select the
+                                 tensor path.  With HLSD_PATH_TENSOR: HLSD_ERR_INVALID                 */
+#define HLSD_FLAG_FUSED 0x200 /* opt-in speed mode of the register-resident kernels (n in 4..128): the
+                                 reference's operations in the reference's order, but a - b*c and the
+                                 Givens pair are contracted into fused multiply-adds (one rounding
+                                 instead of two).  Not bit-identical; residuals as for the exact
+                                 kernels; LU pivots may differ where two candidates tie to round-off.
+                                 Ignored by kernels without a fused form.  With HLSD_FLAG_EXACT:
+                                 HLSD_ERR_INVALID                                                      */
+#define HLSD_FLAG_MASK 0x300
 
 /* ---- host-pointer entry points (the reference's top(), batched) ---- */
 int hlsd_cholesky_host(const float* A, float* L, int n, int64_t batch, int design, int flags);
@@ -86,11 +104,25 @@ int hlsd_lu_dev(const float* dA, float* dL, float* dU, int32_t* dP, int n, int64
 int hlsd_qr_dev(const float* dA, float* dQ, float* dR, int rows, int cols, int64_t batch, int design, int flags,
                 void* stream);
 
+/* ---- one host batch split over several GPUs of the box ----
+ * BASELINE north_star: "the batch is partitioned across the 8 GPUs of one box by plain batch splitting, with no
+ * NCCL on the hot path".  Same arguments and results as the *_host entry points; `devices` lists `ndevices` CUDA
+ * device ordinals (NULL = all visible devices).  The batch is cut into contiguous, balanced spans, one per
+ * device; each span runs the same chunked copy/compute pipeline on its own device from its own worker thread.
+ * Returns the first failure (all spans are still waited for). */
+int hlsd_cholesky_host_multi(const float* A, float* L, int n, int64_t batch, int design, int flags,
+                             const int* devices, int ndevices);
+int hlsd_lu_host_multi(const float* A, float* L, float* U, int32_t* P, int n, int64_t batch, int design, int flags,
+                       const int* devices, int ndevices);
+int hlsd_qr_host_multi(const float* A, float* Q, float* R, int rows, int cols, int64_t batch, int design, int flags,
+                       const int* devices, int ndevices);
+
 /* ---- pinned host buffers for the *_host entry points (optional; pageable memory also works) ---- */
 void* hlsd_host_alloc(size_t bytes);
 void hlsd_host_free(void* p);
-/* The *_host entry points keep their device staging buffers and streams (per calling thread) between
- * calls; this frees them. */
+/* The *_host entry points keep their device staging buffers and streams in a process-wide pool (one set per
+ * concurrent call and device, reused by later calls from any thread), and the blocked paths keep their
+ * workspaces in a library-owned memory pool; this frees everything that is not in use. */
 void hlsd_release_workspace(void);
 
 /* ---- housekeeping ---- */
@@ -103,8 +135,15 @@ const char* hlsd_version(void);
 /* ---- self-checks (diagnostics; no counterpart in the reference) ----
  * The exact kernels divide several numerators by one pivot with a shared reciprocal (csrc/common.cuh).
  * This compares that division with IEEE division, bit for bit, over `count` pairs of DEVICE floats.
- * out2 (device, 2 x int64): [0] = mismatches (must be 0), [1] = pairs served by the fast sequence. */
-int hlsd_selftest_division(const float* num, const float* den, int64_t count, int64_t* out2, void* stream);
+ * out3 (device, 3 x int64): [0] = mismatches (must be 0), [1] = pairs served by the fast sequence,
+ * [2] = informational: mismatches the fast sequence alone would produce without the guard that sends divisors
+ * with an all-ones mantissa to IEEE division. */
+int hlsd_selftest_division(const float* num, const float* den, int64_t count, int64_t* out3, void* stream);
+/* The staging pipeline of the *_host entry points with the kernel launch left out: `units` records of
+ * in_bytes each go host -> device, `units` records of out_bytes each come back (their content is whatever the
+ * staging buffers held).  Measures what the host <-> device links of the box allow for a given record shape;
+ * bench.py reports the e2e leg as a fraction of it. */
+int hlsd_selftest_copy_host(const void* in, void* out, size_t in_bytes, size_t out_bytes, int64_t units);
 
 #ifdef __cplusplus
 }

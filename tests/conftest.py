@@ -38,6 +38,12 @@ def golden_qr():
     return np.load(os.path.join(GOLDEN, "golden_qr.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_large():
+    """Reference outputs on the 256 / 512 operand files (Cholesky/op256.bin ... LU/op512.bin)."""
+    return np.load(os.path.join(GOLDEN, "golden_large.npz"))
+
+
 def bits_equal(a, b):
     a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
     if a.shape != b.shape or a.dtype != b.dtype:

@@ -1,5 +1,5 @@
-// Host-side testbench in the shape of the reference's *_tb.cpp, written against the drop-in
-// headers of this directory: read op<N>.bin row by row with fread (chol_tb.cpp:18-24), call top()
+// TEST CODE (not part of the product package).  Host-side testbench in the shape of the reference's
+// *_tb.cpp, written against the drop-in headers of hls_designs_b200/host/: read op<N>.bin row by row with fread (chol_tb.cpp:18-24), call top()
 // five times (chol_tb.cpp:25-28), rebuild the textbook factorisation in the testbench and compare
 // (template/T_chol_tb.cpp:39-77, LU/lu_v1.1/model4x4/lu_tb.cpp:75-110 and :168-183,
 // QR/qr_v2.1/template/T_qr_tb.cpp), return non-zero on failure.  The operand path is argv[1]

@@ -21,7 +21,7 @@ def _declared_symbols():
 def test_library_exports_every_declared_symbol():
     lib = hd.load()
     declared = _declared_symbols()
-    assert len(declared) >= 13
+    assert len(declared) >= 19
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/hlsd.h but not exported"
     assert sorted(_lib.SIGNATURES) == declared, "python binding and header disagree"
@@ -43,7 +43,14 @@ def test_argument_errors_without_gpu():
     assert lib.hlsd_qr_host(a.ctypes.data, a.ctypes.data, a.ctypes.data, 3, 4, 1, 21, 0) == 1  # rows < cols
     assert lib.hlsd_cholesky_dev(1, 1, 4, 1, 99, 0, None) == 1  # unknown design, checked before any CUDA call
     assert b"design" in lib.hlsd_last_error()
-    assert lib.hlsd_lu_dev(1, 1, 1, 1, 4, 1, 11, 0x100, None) == 1  # unknown flag bits
+    assert lib.hlsd_lu_dev(1, 1, 1, 1, 4, 1, 11, 0x1000, None) == 1  # unknown flag bits
+    assert b"flag" in lib.hlsd_last_error()
+    assert lib.hlsd_lu_dev(1, 1, 1, 1, 4, 1, 11, hd.FLAG_EXACT | hd.FLAG_FUSED, None) == 1  # exclusive
+    assert lib.hlsd_cholesky_dev(1, 1, 256, 1, 13, hd.FLAG_EXACT | hd.PATHS["tensor"], None) == 1
+    assert lib.hlsd_cholesky_host_multi(None, a.ctypes.data, 4, 1, 13, 0, None, 0) == 1
+    devs = (ctypes.c_int * 1)(0)
+    assert lib.hlsd_cholesky_host_multi(a.ctypes.data, a.ctypes.data, 4, 1, 13, 0, devs, 0) == 1  # a device list of length 0
+    assert lib.hlsd_selftest_copy_host(None, a.ctypes.data, 64, 64, 1) == 1
     assert lib.hlsd_cholesky_host(a.ctypes.data, a.ctypes.data, 4, 0, 13, 0) == 0  # empty batch is a no-op
 
 
