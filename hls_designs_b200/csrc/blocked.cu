@@ -612,21 +612,33 @@ static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int
     if ((e = ensure_dynamic_smem(blk_diag_kernel<DIAG_CHOL_INV>, kDiagSmem)) != cudaSuccess) return e;
     const int panels = n / NB;
     const unsigned nb = (unsigned)batch;
-    blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, nb), 256, 0, st>>>(L, n);
-    count_launch();
+    {
+        ProfScope ps(HLSD_PROF_OTHER, st);
+        blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, nb), 256, 0, st>>>(L, n);
+        count_launch();
+    }
     for (int q = 0; q < panels; q++) {
         const int o = q * NB;
         const int mt = panels - q - 1;
         const float* src = (q == 0) ? A : L;  // where block column q currently lives
         if (q > 0) {
-            blk_ll2_kernel<<<dim3((panels - q + 1) / 2, nb), 512, Ll2Smem::kTotal, st>>>(A, L, n, q);
+            {
+                ProfScope ps(HLSD_PROF_UPDATE, st);
+                blk_ll2_kernel<<<dim3((panels - q + 1) / 2, nb), 512, Ll2Smem::kTotal, st>>>(A, L, n, q);
+                count_launch();
+            }
+        }
+        {
+            ProfScope ps(HLSD_PROF_DIAG, st);
+            blk_diag_kernel<DIAG_CHOL_INV><<<nb, 512, kDiagSmem, st>>>(src, L, W, n, o);
             count_launch();
         }
-        blk_diag_kernel<DIAG_CHOL_INV><<<nb, 512, kDiagSmem, st>>>(src, L, W, n, o);
-        count_launch();
         if (mt > 0) {
-            blk_mma_kernel<<<dim3(mt, nb), 256, MmaSmem::kTotal, st>>>(src, L, W, n, o);
-            count_launch();
+            {
+                ProfScope ps(HLSD_PROF_TRSM, st);
+                blk_mma_kernel<<<dim3(mt, nb), 256, MmaSmem::kTotal, st>>>(src, L, W, n, o);
+                count_launch();
+            }
         }
     }
     return cudaGetLastError();
@@ -1122,48 +1134,82 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
     float *Winv = ws, *T0 = ws + w_floats, *T1 = T0 + t_floats;
     const unsigned nb = (unsigned)batch;
     const long nn = (long)n * n;
-    if ((e = cudaMemcpyAsync(U, A, sizeof(float) * (size_t)batch * nn, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) {
+    {
+        ProfScope ps(HLSD_PROF_OTHER, st);
+        e = cudaMemcpyAsync(U, A, sizeof(float) * (size_t)batch * nn, cudaMemcpyDeviceToDevice, st);
+    }
+    if (e != cudaSuccess) {
         ws_free(ws, st);
         return e;
     }
     const int panels = n / NB;
-    blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, nb), 256, 0, st>>>(L, n);
-    count_launch();
+    {
+        ProfScope ps(HLSD_PROF_OTHER, st);
+        blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, nb), 256, 0, st>>>(L, n);
+        count_launch();
+    }
     for (int p = 0; p < panels; p++) {
         const int o = p * NB;
         const int mt = panels - p - 1, ncols = mt * NB;
         // thread = row of the panel: later panels are shorter and run with fewer (cheaper to synchronise) threads
-        lu_panel_kernel<<<nb, std::max(256, n - o), 0, st>>>(U, L, P, n, o);
-        count_launch();
-        if (mt == 0) {  // last panel: nothing to update, only its L columns go back to the reference's convention
-            lu_unswap_panel_kernel<<<nb, kUnswapThreads, unswap_smem, st>>>(L, P, n, o);
+        {
+            ProfScope ps(HLSD_PROF_PANEL, st);
+            lu_panel_kernel<<<nb, std::max(256, n - o), 0, st>>>(U, L, P, n, o);
             count_launch();
+        }
+        if (mt == 0) {  // last panel: nothing to update, only its L columns go back to the reference's convention
+            {
+                ProfScope ps(HLSD_PROF_PERMUTE, st);
+                lu_unswap_panel_kernel<<<nb, kUnswapThreads, unswap_smem, st>>>(L, P, n, o);
+                count_launch();
+            }
             break;
         }
-        lu_swap_kernel<<<dim3((ncols + 127) / 128, nb), 128, n * sizeof(int), st>>>(U, P, n, o);
-        count_launch();
-        blk_diag_kernel<DIAG_INV_ONLY><<<nb, 512, kDiagSmem, st>>>(L, L, Winv, n, o);  // W = inv(L11), L11 unit lower
-        count_launch();
-        lu_transpose_kernel<0><<<dim3(ncols / 32, 4, nb), dim3(32, 8), 0, st>>>(U, T0, n, o);
-        count_launch();
+        {
+            ProfScope ps(HLSD_PROF_PERMUTE, st);
+            lu_swap_kernel<<<dim3((ncols + 127) / 128, nb), 128, n * sizeof(int), st>>>(U, P, n, o);
+            count_launch();
+        }
+        {
+            ProfScope ps(HLSD_PROF_DIAG, st);
+            blk_diag_kernel<DIAG_INV_ONLY><<<nb, 512, kDiagSmem, st>>>(L, L, Winv, n, o);  // W = inv(L11), L11 unit lower
+            count_launch();
+        }
+        {
+            ProfScope ps(HLSD_PROF_PERMUTE, st);
+            lu_transpose_kernel<0><<<dim3(ncols / 32, 4, nb), dim3(32, 8), 0, st>>>(U, T0, n, o);
+            count_launch();
+        }
         TileArgs g{};
         g.A = T0, g.lda = NB, g.strideA = (long)n * NB;
         g.B = Winv, g.ldb = NB, g.strideB = (long)NB * NB;
         g.Csrc = T1, g.Cdst = T1, g.ldc = NB, g.strideC = (long)n * NB;
         g.tiles_col = 1;
-        gemm_tile_kernel<0><<<dim3(mt, nb), 256, MmaSmem::kTotal, st>>>(g);
-        count_launch();
-        lu_transpose_kernel<1><<<dim3(ncols / 32, 4, nb), dim3(32, 8), 0, st>>>(U, T1, n, o);
-        count_launch();
+        {
+            ProfScope ps(HLSD_PROF_TRSM, st);
+            gemm_tile_kernel<0><<<dim3(mt, nb), 256, MmaSmem::kTotal, st>>>(g);
+            count_launch();
+        }
+        {
+            ProfScope ps(HLSD_PROF_PERMUTE, st);
+            lu_transpose_kernel<1><<<dim3(ncols / 32, 4, nb), dim3(32, 8), 0, st>>>(U, T1, n, o);
+            count_launch();
+        }
         TileArgs h{};
         h.A = L + (long)(o + NB) * n + o, h.lda = n, h.strideA = nn;
         h.B = T1, h.ldb = NB, h.strideB = (long)n * NB;
         h.Csrc = U + (long)(o + NB) * n + (o + NB), h.Cdst = U + (long)(o + NB) * n + (o + NB), h.ldc = n, h.strideC = nn;
         h.tiles_col = mt;
-        gemm_tile_kernel<1><<<dim3(mt * mt, nb), 256, MmaSmem::kTotal, st>>>(h);
-        count_launch();
-        lu_unswap_panel_kernel<<<nb, kUnswapThreads, unswap_smem, st>>>(L, P, n, o);  // L21 has served as operand
-        count_launch();
+        {
+            ProfScope ps(HLSD_PROF_UPDATE, st);
+            gemm_tile_kernel<1><<<dim3(mt * mt, nb), 256, MmaSmem::kTotal, st>>>(h);
+            count_launch();
+        }
+        {
+            ProfScope ps(HLSD_PROF_PERMUTE, st);
+            lu_unswap_panel_kernel<<<nb, kUnswapThreads, unswap_smem, st>>>(L, P, n, o);  // L21 has served as operand
+            count_launch();
+        }
     }
     e = cudaGetLastError();
     ws_free(ws, st);

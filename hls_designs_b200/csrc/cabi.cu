@@ -82,6 +82,30 @@ void ws_free(void* p, cudaStream_t st) {
     if (p) cudaFreeAsync(p, st);
 }
 
+// ---- per-launch timing (hlsd_profile_begin / hlsd_profile_end) ----
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
+struct ProfRec {
+    int cls;
+    cudaEvent_t a, b;
+};
+static std::vector<ProfRec> g_prof;
+ProfScope::ProfScope(int c, cudaStream_t s) : cls(c), st(s) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) {
+        if (a) cudaEventDestroy(a);
+        a = b = nullptr;
+        return;
+    }
+    cudaEventRecord(a, st);
+}
+ProfScope::~ProfScope() {
+    if (!a) return;
+    cudaEventRecord(b, st);
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    g_prof.push_back(ProfRec{cls, a, b});
+}
+
 static thread_local std::string g_err = "";
 
 static int fail(hlsd_status st, const std::string& msg) {
@@ -526,6 +550,37 @@ int hlsd_device_count(void) {
 int64_t hlsd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* hlsd_last_error(void) { return g_err.c_str(); }
 const char* hlsd_version(void) { return "hlsd 0.2 (sm_100a)"; }
+
+int hlsd_profile_begin(void) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    for (auto& r : g_prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    g_prof_on.store(true);
+    return 0;
+}
+int hlsd_profile_end(double* ms, int64_t* launches, int n) {
+    g_prof_on.store(false);
+    if (!ms || n < 1) return fail(HLSD_ERR_INVALID, "hlsd_profile_end: bad argument");
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    int rc = 0;
+    for (auto& r : g_prof) {
+        float t = 0.0f;
+        cudaError_t e = cudaEventSynchronize(r.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.a, r.b);
+        if (e != cudaSuccess && !rc) rc = cuda_fail(e, "hlsd_profile_end");
+        if (e == cudaSuccess && r.cls >= 0 && r.cls < n) {
+            ms[r.cls] += t;
+            if (launches) launches[r.cls] += 1;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    return rc;
+}
 
 int hlsd_selftest_division(const float* num, const float* den, int64_t count, int64_t* out3, void* stream) {
     if (!num || !den || !out3 || count < 0) return fail(HLSD_ERR_INVALID, "hlsd_selftest_division: bad argument");

@@ -528,6 +528,7 @@ static cudaError_t chol_dispatch(const float* A, float* L, int n, long batch, in
 
 cudaError_t cholesky_exact(const float* A, float* L, int n, long batch, int variant, int path, int fused, cudaStream_t st) {
     if (batch == 0) return cudaSuccess;
+    ProfScope ps(HLSD_PROF_EXACT, st);
     if (fused)
         return variant == 1 ? chol_dispatch<1, true>(A, L, n, batch, path, st) : chol_dispatch<0, true>(A, L, n, batch, path, st);
     return variant == 1 ? chol_dispatch<1, false>(A, L, n, batch, path, st) : chol_dispatch<0, false>(A, L, n, batch, path, st);

@@ -16,6 +16,18 @@ template <class K>
 inline cudaError_t ensure_dynamic_smem(K* kernel, size_t bytes) {
     return ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), bytes);
 }
+// Per-launch timing for hlsd_profile_begin/_end (include/hlsd.h): when profiling is on, a ProfScope brackets the
+// launches issued during its lifetime with two CUDA events on their stream and files the pair under `cls`
+// (HLSD_PROF_*); when it is off (the default) it costs one relaxed atomic load.
+struct ProfScope {
+    ProfScope(int cls, cudaStream_t st);
+    ~ProfScope();
+    ProfScope(const ProfScope&) = delete;
+    ProfScope& operator=(const ProfScope&) = delete;
+    int cls;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+};
 // stream-ordered workspace memory from a library-owned pool (the device's default pool is left alone)
 cudaError_t ws_alloc(void** p, size_t bytes, cudaStream_t st);
 void ws_free(void* p, cudaStream_t st);

@@ -681,6 +681,7 @@ static cudaError_t lu_dispatch(const float* A, float* L, float* U, int* P, int n
 cudaError_t lu_exact(const float* A, float* L, float* U, int* P, int n, long batch, int pivoting, int path, int fused,
                      cudaStream_t st) {
     if (batch == 0) return cudaSuccess;
+    ProfScope ps(HLSD_PROF_EXACT, st);
     return fused ? lu_dispatch<true>(A, L, U, P, n, batch, pivoting, path, st)
                  : lu_dispatch<false>(A, L, U, P, n, batch, pivoting, path, st);
 }

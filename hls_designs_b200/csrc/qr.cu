@@ -807,6 +807,7 @@ static cudaError_t qr_dispatch(const float* A, float* Q, float* R, int rows, int
 cudaError_t qr_exact(const float* A, float* Q, float* R, int rows, int cols, long batch, int variant, int path, int fused,
                      cudaStream_t st) {
     if (batch == 0) return cudaSuccess;
+    ProfScope ps(HLSD_PROF_EXACT, st);
     if (variant == 1) return qr_dispatch<1, false>(A, Q, R, rows, cols, batch, path, st);  // qr_v1.x: exact only
     return fused ? qr_dispatch<0, true>(A, Q, R, rows, cols, batch, path, st)
                  : qr_dispatch<0, false>(A, Q, R, rows, cols, batch, path, st);

@@ -132,6 +132,22 @@ int64_t hlsd_launch_count(void);           /* kernels launched by this library s
 const char* hlsd_last_error(void);         /* thread-local, never NULL */
 const char* hlsd_version(void);
 
+/* ---- per-kernel-class timing of the blocked paths (diagnostic; used by bench.py for the roofline of the dominant
+ * kernel).  Between hlsd_profile_begin() and hlsd_profile_end() every kernel launch of the library is bracketed by
+ * CUDA events on its stream; hlsd_profile_end() waits for them and ADDS the elapsed milliseconds per class to
+ * ms[0..n-1] (classes >= n are dropped) and the launch counts to launches[0..n-1] (may be NULL).  Process-wide; not
+ * meant to stay on in production (two events per launch). */
+#define HLSD_PROF_OTHER 0    /* zero fill, copies of the working matrix                                      */
+#define HLSD_PROF_UPDATE 1   /* tcgen05 trailing update: blk_ll2_kernel (Cholesky), gemm_tile_kernel<1> (LU)  */
+#define HLSD_PROF_DIAG 2     /* SIMT diagonal block: Cholesky + inverse / inverse of the unit-lower LU block   */
+#define HLSD_PROF_TRSM 3     /* tcgen05 panel solve: blk_mma_kernel (Cholesky), gemm_tile_kernel<0> (LU)       */
+#define HLSD_PROF_PANEL 4    /* SIMT pivoted panel factorisation of the blocked LU                            */
+#define HLSD_PROF_PERMUTE 5  /* row exchanges, un-exchanges and transposes of the blocked LU                   */
+#define HLSD_PROF_EXACT 6    /* the exact (register / shared-memory / global) kernels                          */
+#define HLSD_PROF_CLASSES 7
+int hlsd_profile_begin(void);
+int hlsd_profile_end(double* ms, int64_t* launches, int n);
+
 /* ---- self-checks (diagnostics; no counterpart in the reference) ----
  * The exact kernels divide several numerators by one pivot with a shared reciprocal (csrc/common.cuh).
  * This compares that division with IEEE division, bit for bit, over `count` pairs of DEVICE floats.

@@ -1,6 +1,7 @@
-"""CPU test of the multi-GPU plan (no data-path collective: plain batch splitting).  Two gloo ranks
-shard a batch with the same helper bench.py uses, and the per-rank counts/timings combine into the
-whole-job throughput exactly as bench.py reports it."""
+"""CPU test of the multi-GPU plan (no data-path collective: plain batch splitting).  Two gloo ranks take
+their share of the work through the very function bench.py's timed legs call (`rank_batch`: the full batch per
+rank under weak scaling, a `shard_batch` span of one batch under --scaling strong), and the per-rank
+counts/timings combine into the whole-job throughput exactly as bench.py reports it."""
 import os
 import socket
 import sys
@@ -11,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bench import combine_ranks, shard_batch  # noqa: E402
+from bench import combine_ranks, rank_batch, shard_batch  # noqa: E402
 
 
 def test_shard_batch_covers_everything_once():
@@ -24,13 +25,21 @@ def test_shard_batch_covers_everything_once():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_rank_batch_weak_and_strong():
+    for world in (1, 2, 4, 8):
+        assert [rank_batch(4096, r, world, "weak") for r in range(world)] == [4096] * world
+        assert sum(rank_batch(4097, r, world, "strong") for r in range(world)) == 4097
+        assert rank_batch(4097, 0, world, "strong") == shard_batch(4097, 0, world)[1]
+
+
 def _worker(rank, world, port):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    start, end = shard_batch(1001, rank, world)
     ms = 10.0 if rank == 0 else 20.0  # rank 1 is slower: the job is as slow as the slowest rank
-    total, worst_ms = combine_ranks(end - start, ms, torch.device("cpu"))
+    total, worst_ms = combine_ranks(rank_batch(1001, rank, world, "strong"), ms, torch.device("cpu"))
     assert total == 1001 and worst_ms == 20.0
+    total, worst_ms = combine_ranks(rank_batch(1001, rank, world, "weak"), ms, torch.device("cpu"))
+    assert total == 2002 and worst_ms == 20.0
     dist.destroy_process_group()
 
 
