@@ -30,6 +30,7 @@ SIGNATURES = {
     "hlsd_launch_count": (_i64, []),
     "hlsd_last_error": (ctypes.c_char_p, []),
     "hlsd_version": (ctypes.c_char_p, []),
+    "hlsd_set_option": (_i, [_i, _i]),
     "hlsd_profile_begin": (_i, []),
     "hlsd_profile_end": (_i, [_vp, _vp, _i]),
     "hlsd_selftest_division": (_i, [_vp, _vp, _i64, _vp, _vp]),

@@ -148,6 +148,14 @@ def qr(A, design="qr_v2.1", path="auto", exact=False, fused=False, devices=None)
     return Q, R
 
 
+OPTIONS = {"chol_slab": 1, "lu32_kernel": 2, "diag_kernel": 3, "lockstep": 4}
+
+
+def set_option(name, value):
+    """Measurement switch (include/hlsd.h, HLSD_OPT_*): selects the alternative kernel where two serve a request."""
+    _lib.check(_lib.load().hlsd_set_option(OPTIONS[name], int(value)))
+
+
 def launch_count():
     return int(_lib.load().hlsd_launch_count())
 

@@ -14,6 +14,9 @@
 
 namespace hlsd {
 
+static std::atomic<int> g_options[HLSD_OPT_COUNT];
+int option(int key) { return (key >= 0 && key < HLSD_OPT_COUNT) ? g_options[key].load(std::memory_order_relaxed) : 0; }
+
 static std::atomic<int64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -332,13 +335,19 @@ static void ws_release_idle() {
     if (have_cur) cudaSetDevice(cur);
 }
 
-// Chunk size of the staging pipeline: about kChunkBytes of arguments per chunk, at least one matrix, and - so that
-// the copy-in of chunk i+1, the kernels of chunk i and the copy-out of chunk i-1 can overlap - no more than a
-// third of the batch when the batch is large enough to be worth splitting.  Every chunk is copied to the BASE of
-// its staging buffers (cudaMalloc alignment), so chunk starts need no alignment of their own.
+// Chunk size of the staging pipeline: about kChunkBytes of arguments per chunk, but at least one matrix per SM
+// (the kernels for n >= 128 give every matrix one CTA or a few: a chunk of 5 matrices of 1024 x 1024 left the GPU
+// 95 % idle and the pipeline kernel-bound at half the PCIe rate) as long as that stays under kMaxChunkBytes; never
+// more than the batch; and - so that the copy-in of chunk i+1, the kernels of chunk i and the copy-out of chunk
+// i-1 can overlap - no more than a third of the batch when the batch is large enough to be worth splitting.
+// Every chunk is copied to the BASE of its staging buffers (cudaMalloc alignment), so chunk starts need no
+// alignment of their own.
 static int64_t staging_chunk(int64_t batch, size_t per_matrix) {
-    const size_t kChunkBytes = (size_t)64 << 20, kMinSplitBytes = (size_t)8 << 20;
-    int64_t chunk = (int64_t)(kChunkBytes / (per_matrix ? per_matrix : 1));
+    const size_t kChunkBytes = (size_t)64 << 20, kMaxChunkBytes = (size_t)2 << 30, kMinSplitBytes = (size_t)8 << 20;
+    if (per_matrix == 0) per_matrix = 1;
+    int64_t chunk = (int64_t)(kChunkBytes / per_matrix);
+    const int64_t fill = sm_count() > 0 ? sm_count() : 148;
+    if (chunk < fill) chunk = std::min<int64_t>(fill, (int64_t)(kMaxChunkBytes / per_matrix));
     if (chunk < 1) chunk = 1;
     if (chunk > batch) chunk = batch;
     if (chunk == batch && batch >= 3 && (size_t)batch * per_matrix >= 3 * kMinSplitBytes) chunk = (batch + 2) / 3;
@@ -550,6 +559,12 @@ int hlsd_device_count(void) {
 int64_t hlsd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* hlsd_last_error(void) { return g_err.c_str(); }
 const char* hlsd_version(void) { return "hlsd 0.2 (sm_100a)"; }
+
+int hlsd_set_option(int opt, int value) {
+    if (opt < 1 || opt >= HLSD_OPT_COUNT) return fail(HLSD_ERR_INVALID, "unknown option");
+    g_options[opt].store(value);
+    return 0;
+}
 
 int hlsd_profile_begin(void) {
     std::lock_guard<std::mutex> lock(g_prof_mu);

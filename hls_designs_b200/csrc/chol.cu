@@ -152,41 +152,93 @@ chol_tpm_kernel(const float* __restrict__ A, float* __restrict__ L, long batch) 
 // and the column is all-gathered by one shuffle per row (the "column update" stream).
 // Entries a[t][j] with j > row index are scratch (computed, never stored).
 // ------------------------------------------------------------------------------------------------
-template <int N, int R, int VARIANT, int WARPS, bool FUSED>
+// PACKED: the slab holds only the lower triangle, row i rounded up to whole 16-byte pieces (i/4 + 1 of them), so a
+// 32 x 32 matrix takes 2.3 KB instead of 4 KB and twice as many warps fit on an SM (the kernel is latency bound:
+// 6 warps per SM gave 0.47 of the HBM roofline).  Every row arrives by its own bulk copy (only the pieces that
+// hold a_ij, j <= i: 44 % less operand traffic too) and leaves by one bulk store for its data pieces and one, from
+// a shared block of zeros, for the pieces right of the diagonal.
+template <int N>
+struct PackedTri {
+    static constexpr int G = N / 4;
+    static constexpr int kPieces = 2 * G * (G + 1);           // 16-byte pieces per matrix
+    static constexpr int kSlot = (kPieces + 1) * 4;           // floats; +1 piece: consecutive slots start in different banks
+    __host__ __device__ static constexpr int row_off(int i) {  // first piece of row i
+        return (i / 4 + 1) * (2 * (i / 4) + i % 4);
+    }
+};
+
+// LOCKSTEP: one CTA-wide barrier per elimination step.  The step loop is unrolled at compile time (register arrays
+// can only be indexed by constants), so a 64 x 64 factorisation is ~190 KB of straight-line code that every warp
+// walks through once per slab; with the warps of an SM at different places in it, instruction fetch becomes the
+// top stall (ncu: `no_instruction` 3.6 warps per issue at N = 64).  In lockstep all warps fetch the same lines at
+// the same time.  Needs the same number of slab iterations in every warp of a CTA (idle ones run on `valid = 0`).
+template <int N, int R, int VARIANT, int WARPS, bool FUSED, bool PACKED = false, bool LOCKSTEP = false>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 chol_rows_kernel(const float* __restrict__ A, float* __restrict__ L, long batch) {
     using Cfg = TpmCfg<N>;
+    using Tri = PackedTri<N>;
     constexpr int MPW = 32 / R;  // matrices per warp
     constexpr int T = N / R;     // local rows per lane
+    constexpr int kSlotFloats = PACKED ? Tri::kSlot : Cfg::kSlot;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* slabs = reinterpret_cast<float*>(smem_raw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * MPW * Cfg::kSlot * 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * MPW * kSlotFloats * 4);
+    __shared__ __align__(16) float zeros[PACKED ? N : 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = lane % R, m = lane / R, gbase = lane - r;
-    float* slot = slabs + ((size_t)warp * MPW + m) * Cfg::kSlot;
+    float* slot = slabs + ((size_t)warp * MPW + m) * kSlotFloats;
     uint64_t* bar = bars + warp;
     if (lane == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
     }
+    if constexpr (PACKED) {
+        if (threadIdx.x < N) zeros[threadIdx.x] = 0.0f;
+        fence_async_smem();
+        __syncthreads();
+    }
     __syncwarp();
     const long num_slabs = (batch + MPW - 1) / MPW;
-    constexpr uint32_t kPart = Cfg::kMatBytes / R;  // each lane of a group moves 1/R of the matrix
+    constexpr uint32_t kPart = Cfg::kMatBytes / R;  // dense layout: each lane of a group moves 1/R of the matrix
     uint32_t parity = 0;
-    for (long s = (long)blockIdx.x * WARPS + warp; s < num_slabs; s += (long)gridDim.x * WARPS) {
+    for (long s0 = (long)blockIdx.x * WARPS; s0 < num_slabs; s0 += (long)gridDim.x * WARPS) {
+        const long s = s0 + warp;
+        if (!LOCKSTEP && s >= num_slabs) break;
         const long m0 = s * MPW;
-        const int valid = (int)min((long)MPW, batch - m0);
+        const int valid = s < num_slabs ? (int)min((long)MPW, batch - m0) : 0;
         bulk_wait_read<0>();
         __syncwarp();  // all lanes' previous stores have drained before anyone refills the slab
-        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * Cfg::kMatBytes);
+        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * (PACKED ? Tri::kPieces * 16 : Cfg::kMatBytes));
         __syncwarp();
-        // each lane moves 1/R of its matrix: many small copies in flight measured faster than one per matrix
-        if (m < valid) bulk_g2s(slot + r * (kPart / 4), A + (m0 + m) * (long)(N * N) + r * (kPart / 4), kPart, bar);
-        mbar_wait(bar, parity);
-        parity ^= 1;
         // a[t][j]: row i = t*R + r, columns 0 .. t*R + R - 1 (static bound; j > i is scratch)
         float a[T][N];
-        {
+        if constexpr (PACKED) {
+            if (m < valid) {
+#pragma unroll
+                for (int t = 0; t < T; t++) {
+                    const int i = t * R + r;
+                    bulk_g2s(slot + Tri::row_off(i) * 4, A + (m0 + m) * (long)(N * N) + i * N, (uint32_t)(i / 4 + 1) * 16, bar);
+                }
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1;
+#pragma unroll
+            for (int t = 0; t < T; t++) {
+                const int i = t * R + r;
+                const float4* s4 = reinterpret_cast<const float4*>(slot) + Tri::row_off(i);
+#pragma unroll
+                for (int q = 0; q < (t * R + R + 3) / 4; q++) {
+                    // pieces right of the diagonal piece are not in the slab: those registers stay scratch
+                    float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (R == 4 || q <= i / 4) v = s4[q];
+                    a[t][4 * q] = v.x, a[t][4 * q + 1] = v.y, a[t][4 * q + 2] = v.z, a[t][4 * q + 3] = v.w;
+                }
+            }
+        } else {
+            // each lane moves 1/R of its matrix: many small copies in flight measured faster than one per matrix
+            if (m < valid) bulk_g2s(slot + r * (kPart / 4), A + (m0 + m) * (long)(N * N) + r * (kPart / 4), kPart, bar);
+            mbar_wait(bar, parity);
+            parity ^= 1;
             const float4* s4 = reinterpret_cast<const float4*>(slot);
 #pragma unroll
             for (int t = 0; t < T; t++) {
@@ -201,6 +253,7 @@ chol_rows_kernel(const float* __restrict__ A, float* __restrict__ L, long batch)
         static_for<0, N>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
             constexpr int tk = k / R, rk = k % R;
+            if constexpr (LOCKSTEP) __syncthreads();
             // pivot: owner lane rk, local row tk
             // lanes that do not own row k hold scratch there (possibly zero or negative): they root 1.0 instead,
             // so that no lane leaves the fast path of the square root
@@ -263,28 +316,59 @@ chol_rows_kernel(const float* __restrict__ A, float* __restrict__ L, long batch)
                 }
             }
         }
-        if (m < valid) {
-            float4* d4 = reinterpret_cast<float4*>(slot);
+        if constexpr (PACKED) {
+            if (m < valid) {
 #pragma unroll
-            for (int t = 0; t < T; t++) {
-                const int i = t * R + r;
+                for (int t = 0; t < T; t++) {
+                    const int i = t * R + r;
+                    float4* d4 = reinterpret_cast<float4*>(slot) + Tri::row_off(i);
 #pragma unroll
-                for (int q = 0; q < N / 4; q++) {
-                    float e[4];
+                    for (int q = 0; q < (t * R + R + 3) / 4; q++) {
+                        float e[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int j = 4 * q + u;
-                        e[u] = (j < t * R + R && j <= i) ? a[t][j < t * R + R ? j : 0] : 0.0f;
+                        for (int u = 0; u < 4; u++) {
+                            const int j = 4 * q + u;
+                            e[u] = (j < t * R + R && j <= i) ? a[t][j < t * R + R ? j : 0] : 0.0f;
+                        }
+                        if (R == 4 || q <= i / 4) d4[q] = make_float4(e[0], e[1], e[2], e[3]);
                     }
-                    d4[i * (N / 4) + q] = make_float4(e[0], e[1], e[2], e[3]);
                 }
+                fence_async_smem();
+                // every lane stores the rows it wrote itself: the data pieces, then zeros for the rest of the row
+#pragma unroll
+                for (int t = 0; t < T; t++) {
+                    const int i = t * R + r;
+                    float* dst = L + (m0 + m) * (long)(N * N) + i * N;
+                    const int pieces = i / 4 + 1;
+                    bulk_s2g(dst, slot + Tri::row_off(i) * 4, (uint32_t)pieces * 16);
+                    if (pieces < N / 4) bulk_s2g(dst + pieces * 4, zeros, (uint32_t)(N / 4 - pieces) * 16);
+                }
+                bulk_commit();
             }
-            fence_async_smem();
-        }
-        __syncwarp();  // the whole matrix (all R lanes' rows) is in the slot
-        if (m < valid) {
-            bulk_s2g(L + (m0 + m) * (long)(N * N) + r * (kPart / 4), slot + r * (kPart / 4), kPart);
-            bulk_commit();
+        } else {
+            if (m < valid) {
+                float4* d4 = reinterpret_cast<float4*>(slot);
+#pragma unroll
+                for (int t = 0; t < T; t++) {
+                    const int i = t * R + r;
+#pragma unroll
+                    for (int q = 0; q < N / 4; q++) {
+                        float e[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int j = 4 * q + u;
+                            e[u] = (j < t * R + R && j <= i) ? a[t][j < t * R + R ? j : 0] : 0.0f;
+                        }
+                        d4[i * (N / 4) + q] = make_float4(e[0], e[1], e[2], e[3]);
+                    }
+                }
+                fence_async_smem();
+            }
+            __syncwarp();  // the whole matrix (all R lanes' rows) is in the slot
+            if (m < valid) {
+                bulk_s2g(L + (m0 + m) * (long)(N * N) + r * (kPart / 4), slot + r * (kPart / 4), kPart);
+                bulk_commit();
+            }
         }
     }
     bulk_wait_read<0>();
@@ -445,12 +529,14 @@ static cudaError_t launch_tpm_w(const float* A, float* L, long batch, cudaStream
     return cudaGetLastError();
 }
 
-template <int N, int R, int VARIANT, int WARPS, bool FUSED>
+template <int N, int R, int VARIANT, int WARPS, bool FUSED, bool PACKED = false, bool LOCKSTEP = false>
 static cudaError_t launch_rows(const float* A, float* L, long batch, cudaStream_t st) {
     using Cfg = TpmCfg<N>;
     constexpr int MPW = 32 / R;
-    const size_t smem = (size_t)WARPS * MPW * Cfg::kSlot * 4 + WARPS * sizeof(uint64_t);
-    auto kern = chol_rows_kernel<N, R, VARIANT, WARPS, FUSED>;
+    constexpr int kSlotFloats = PACKED ? PackedTri<N>::kSlot : Cfg::kSlot;
+    constexpr size_t smem = (size_t)WARPS * MPW * kSlotFloats * 4 + WARPS * sizeof(uint64_t);
+    static_assert(smem <= 227 * 1024, "slabs do not fit");
+    auto kern = chol_rows_kernel<N, R, VARIANT, WARPS, FUSED, PACKED, LOCKSTEP>;
     cudaError_t e = ensure_dynamic_smem(kern, smem);
     if (e != cudaSuccess) return e;
     const long num_slabs = (batch + MPW - 1) / MPW;
@@ -469,9 +555,21 @@ static cudaError_t launch_tpm(const float* A, float* L, long batch, cudaStream_t
     } else if constexpr (N == 32) {
         // measured (fraction of HBM peak): 4 lanes per matrix 0.47, 8 lanes 0.39, 16 lanes 0.31: fewer lanes per matrix
         // mean fewer shuffles per useful operation, even at half the warps per SM
-        return launch_rows<N, 4, VARIANT, 6, FUSED>(A, L, batch, st);
+        // Packed lower-triangle slabs (12 warps per SM instead of 6) measured SLOWER here: 0.37 of the HBM roofline with
+        // 12 warps (168 registers, ~170 words spilled), 0.33 with 8 warps (no spills), against 0.465 for the dense
+        // slab: a row-wise packed slab costs 23 bulk copies of 16..128 bytes per lane and matrix instead of 2 of 1 KB.
+        // (At N = 64 the same change is 6 copies per lane and wins: 0.181 vs 0.155.)
+        if (option(HLSD_OPT_CHOL_SLAB) == 1) return launch_rows<N, 4, VARIANT, 12, FUSED, true>(A, L, batch, st);
+        if (option(HLSD_OPT_CHOL_SLAB) == 2) return launch_rows<N, 4, VARIANT, 8, FUSED, true>(A, L, batch, st);
+        // one CTA-wide barrier per step (LOCKSTEP) measured +5 % here (0.468 -> 0.490), -1 % at N = 64
+        if (option(HLSD_OPT_LOCKSTEP) == 1) return launch_rows<N, 4, VARIANT, 6, FUSED>(A, L, batch, st);
+        return launch_rows<N, 4, VARIANT, 6, FUSED, false, true>(A, L, batch, st);
     } else if constexpr (N == 64) {
-        return launch_rows<N, 32, VARIANT, 12, FUSED>(A, L, batch, st);  // 16 lanes per matrix measured slower (0.152 vs 0.168)
+        // (16 lanes per matrix measured slower than 32: 0.152 vs 0.168)
+        if (option(HLSD_OPT_CHOL_SLAB) == 1) return launch_rows<N, 32, VARIANT, 12, FUSED>(A, L, batch, st);
+        // packed slabs: 16 warps per SM instead of 12 (20 would cap the kernel at 96 registers: 2 KB of spills)
+        if (option(HLSD_OPT_LOCKSTEP) == 1) return launch_rows<N, 32, VARIANT, 16, FUSED, true, true>(A, L, batch, st);
+        return launch_rows<N, 32, VARIANT, 16, FUSED, true>(A, L, batch, st);
     } else {
         return launch_tpm_w<N, VARIANT, 8, FUSED>(A, L, batch, st);
     }

@@ -7,6 +7,7 @@
 
 namespace hlsd {
 
+int option(int key);  // hlsd_set_option() value (0 = default)
 void count_launch();  // bumps the process-wide launch counter reported by hlsd_launch_count()
 int sm_count();
 // cudaFuncAttributeMaxDynamicSharedMemorySize, issued once per (kernel, device) - again only if a later call needs

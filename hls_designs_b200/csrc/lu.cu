@@ -7,7 +7,7 @@
 // Kernels:
 //   lu_tpm_kernel<N>      thread-per-matrix in registers, N = 4: staged slabs.
 //   lu_regs_kernel<N,R>   R lanes per matrix, all in registers, N in {8, 16, 32}: pivot row by shuffle.
-//   lu_lane_kernel<N>     one lane per row, N = 64 (two warps per matrix).
+//   lu_lane_kernel<N>     one lane per row, N = 64 (two warps per matrix) and N = 128 (four).
 //   lu_group_kernel<G>    G threads per matrix, matrix resident in shared memory.
 //   lu_global_kernel      one CTA per matrix, in place in global memory (any N; exact; slow).
 #include "common.cuh"
@@ -264,28 +264,33 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
             }
             const unsigned bal = __ballot_sync(0xffffffffu, mine);
             const int owner = gbase + __ffs((bal >> gbase) & (R == 32 ? 0xffffffffu : (1u << (R & 31)) - 1u)) - 1;
-            // pivot row: selected from the owner's rows, broadcast over the group, stored as row k of U
-            float own[N];
+            // pivot row: selected from the owner's rows and broadcast over the group (the systolic "pivot broadcast")
 #pragma unroll
             for (int j = k; j < N; j++) {
                 float v = a[0][j];
 #pragma unroll
                 for (int t = 1; t < T; t++) v = isp[t] ? a[t][j] : v;
-                own[j] = v;
                 u[j] = __shfl_sync(0xffffffffu, v, owner);
             }
-            if (U_DIRECT ? (mine && m < valid) : mine) {
+            // ... and stored as row k of U: every lane holds it now, so lane q % R stores quad q - one predicated
+            // 16-byte store per lane instead of N/4 masked stores by the owner alone inside a divergent block
+            {
                 float4* u4 = U_DIRECT ? reinterpret_cast<float4*>(U + (m0 + m) * (long)(N * N) + k * N)
                                       : reinterpret_cast<float4*>(sU + k * N);
-                if constexpr (U_DIRECT) {
-#pragma unroll
-                    for (int q = 0; q < k / 4; q++) __stcs(u4 + q, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
-                }
-#pragma unroll
-                for (int q = k / 4; q < N / 4; q++)
-                    u4[q] = make_float4(4 * q >= k ? own[4 * q >= k ? 4 * q : k] : 0.0f,
-                                        4 * q + 1 >= k ? own[4 * q + 1 >= k ? 4 * q + 1 : k] : 0.0f,
-                                        4 * q + 2 >= k ? own[4 * q + 2 >= k ? 4 * q + 2 : k] : 0.0f, own[4 * q + 3]);
+                static_for<(U_DIRECT ? 0 : k / 4), N / 4>([&](auto qc) {
+                    constexpr int q = decltype(qc)::value;
+                    const float4 v = make_float4(4 * q >= k ? u[4 * q >= k ? 4 * q : k] : 0.0f,
+                                                 4 * q + 1 >= k ? u[4 * q + 1 >= k ? 4 * q + 1 : k] : 0.0f,
+                                                 4 * q + 2 >= k ? u[4 * q + 2 >= k ? 4 * q + 2 : k] : 0.0f,
+                                                 4 * q + 3 >= k ? u[4 * q + 3] : 0.0f);
+                    if (r == q % R) {
+                        if constexpr (U_DIRECT) {
+                            if (m < valid) __stcs(u4 + q, v);
+                        } else {
+                            u4[q] = v;
+                        }
+                    }
+                });
             }
             if constexpr (k < N - 1) {
                 const float piv = u[k];
@@ -332,33 +337,45 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// One lane per row (N = 64: two warps per matrix): position tracking as in lu_regs_kernel with a
-// single data row per lane, the step loop unrolled at compile time.  The pivot row is published
-// through a double-buffered shared-memory row (its owner also stores it straight to global memory as
-// row k of U); the per-warp search partials of the two warps meet in shared memory.  Two named
-// barriers per column (after the partials, after the pivot row); the butterfly of the next column's
-// search is issued right after that column is updated and overlaps the rest of the update.
+// One lane per row (N = 64: two warps per matrix, N = 128: four): position tracking as in lu_regs_kernel with a
+// single data row per lane, the step loop unrolled at compile time.  ONE named barrier per column: every warp
+// reduces its own candidates by butterfly, and its local winner publishes (candidate, data row) in the warp's
+// slot of a buffer that is double-buffered by the parity of k; after the barrier every lane reduces the
+// WPM slot candidates itself and reads the winning slot's row.  The butterfly of the next column's search is
+// issued right after that column is updated and overlaps the rest of the update.
+// Round-2 changes, from the ncu capture of the round-1 kernel (profiles/r02_lu64_baseline_ncu_summary.txt: 43 %
+// of the shared-memory wavefronts were bank conflicts, issue slots 40 % busy with `short_scoreboard`, `barrier`
+// and `mio_throttle` on top): (1) the multipliers are scattered into a slab with an ODD row stride (N + 1 floats:
+// lanes at distinct positions hit distinct banks; with stride N all 32 stores of a column went to one bank);
+// the slab is written out row by row by the matrix's own threads, which also supply the unit diagonal and the
+// zeros, so it needs no initialisation; (2) row k of U is stored by all N threads together (one coalesced
+// element each) instead of by the pivot lane alone inside a divergent block (16 masked float4 stores per
+// column executed for one lane); (3) one barrier per column instead of two.
 // ------------------------------------------------------------------------------------------------
-template <int N, int MATS, bool PIVOT, bool FUSED>
+// LOCKSTEP: the per-matrix barrier becomes a CTA-wide one, so that all matrices of a CTA walk through the unrolled
+// code together (see chol_rows_kernel: instruction fetch is the top stall of the 128 x 128 kernel).
+template <int N, int MATS, bool PIVOT, bool FUSED, bool LOCKSTEP = false>
 __global__ void __launch_bounds__(MATS * N, 1)
 lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restrict__ U, int* __restrict__ P,
                long batch) {
-    static_assert(N == 32 || N == 64, "one or two warps per matrix");
+    static_assert(N == 32 || N == 64 || N == 128, "one, two or four warps per matrix");
     constexpr int WPM = N / 32;  // warps per matrix
-    constexpr int kSlot = N * N + 4;
-    constexpr int kPerMat = kSlot + 2 * N + N + 8;  // floats: A/L slab, 2 pivot-row buffers, P, partials
+    constexpr int LD = N + 1;    // odd row stride of the L slab
+    constexpr int kPerMat = N * LD + 2 * WPM * N + N + 4 * WPM;  // floats: slab, row slots, P, candidates
+    static_assert((N * LD) % 4 == 0 && kPerMat % 4 == 0, "16-byte alignment of the pieces");
     constexpr uint32_t kRowBytes = N * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* base = reinterpret_cast<float*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)MATS * kPerMat * 4);
-    const int mat = threadIdx.x / N, r = threadIdx.x % N, lane = threadIdx.x & 31;
-    float* sA = base + (size_t)mat * kPerMat;
-    float* sRow = sA + kSlot;  // [2][N]: the pivot row of step k in buffer k & 1
-    int* sP = reinterpret_cast<int*>(sRow + 2 * N);
+    const int mat = threadIdx.x / N, r = threadIdx.x % N, lane = threadIdx.x & 31, wim = r >> 5;
+    float* sA = base + (size_t)mat * kPerMat;  // operand rows (dense, stride N) while loading, then the L slab (stride LD)
+    float* sRow = sA + N * LD;                 // [2 parities][WPM slots][N]: candidate pivot rows
+    int* sP = reinterpret_cast<int*>(sRow + 2 * WPM * N);
     PivotCand* part = reinterpret_cast<PivotCand*>(sP + N);  // [2 parities][WPM]
     uint64_t* bar = bars + mat;
     auto gsync = [&]() {
-        if constexpr (WPM == 1) __syncwarp();
+        if constexpr (LOCKSTEP) __syncthreads();
+        else if constexpr (WPM == 1) __syncwarp();
         else named_bar_sync(1 + mat, N);
     };
     if (r == 0) {
@@ -367,12 +384,16 @@ lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
     }
     gsync();
     uint32_t parity = 0;
-    for (long b = (long)blockIdx.x * MATS + mat; b < batch; b += (long)gridDim.x * MATS) {
-        bulk_wait_read<0>();
+    for (long b0 = (long)blockIdx.x * MATS; b0 < batch; b0 += (long)gridDim.x * MATS) {
+        const long b = b0 + mat;
+        const bool live = b < batch;  // (LOCKSTEP: idle matrices of the last round keep step with the others)
+        if (!LOCKSTEP && !live) break;
+        bulk_wait_read<0>();   // the previous matrix's P has left
+        fence_async_smem();    // ... and its slab was read with ordinary loads: order them before the bulk copies below
         gsync();
-        if (r == 0) mbar_arrive_expect_tx(bar, N * kRowBytes);
+        if (r == 0) mbar_arrive_expect_tx(bar, live ? N * kRowBytes : 0);
         gsync();
-        bulk_g2s(sA + r * N, A + b * (long)(N * N) + r * N, kRowBytes, bar);
+        if (live) bulk_g2s(sA + r * N, A + b * (long)(N * N) + r * N, kRowBytes, bar);
         mbar_wait(bar, parity);
         parity ^= 1;
         float a[N];
@@ -384,17 +405,9 @@ lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
                 a[4 * q] = v.x, a[4 * q + 1] = v.y, a[4 * q + 2] = v.z, a[4 * q + 3] = v.w;
             }
         }
-        gsync();  // operand in registers: the slab becomes L (identity)
-        {
-            float4* l4 = reinterpret_cast<float4*>(sA + r * N);
-#pragma unroll
-            for (int q = 0; q < N / 4; q++)
-                l4[q] = make_float4(r == 4 * q ? 1.0f : 0.0f, r == 4 * q + 1 ? 1.0f : 0.0f, r == 4 * q + 2 ? 1.0f : 0.0f,
-                                    r == 4 * q + 3 ? 1.0f : 0.0f);
-        }
         float* ug = U + b * (long)(N * N);  // U rows go straight to global memory, one finished row per step
         int pos = r;
-        gsync();
+        gsync();  // operand in registers: the buffer becomes the L slab
         // this warp's best candidate of column k (rows at positions >= k)
         auto search = [&](auto kc) -> PivotCand {
             constexpr int k = decltype(kc)::value;
@@ -412,32 +425,41 @@ lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
         PivotCand cand = search(std::integral_constant<int, 0>{});
         static_for<0, N>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
-            int p = k;
-            if constexpr (PIVOT && k < N - 1) {
-                if constexpr (WPM == 2) {
-                    PivotCand* pp = part + (k & 1) * 2;
-                    if (lane == 0) pp[r >> 5] = cand;
-                    gsync();
-                    cand = pivot_better(pp[0], pp[1]);
+            constexpr bool kSearch = PIVOT && k < N - 1;
+            float* slots = sRow + (k & 1) * WPM * N;
+            // publish: the warp's local winner (or, without a search, the lane at position k) offers its row
+            const bool offer = kSearch ? (pos == cand.i) : (pos == k);
+            if (offer) {
+                float4* dst = reinterpret_cast<float4*>(slots + (kSearch ? wim : 0) * N);
+#pragma unroll
+                for (int q = k / 4; q < N / 4; q++) dst[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+            }
+            if constexpr (kSearch && WPM > 1) {
+                if (lane == 0) part[(k & 1) * WPM + wim] = cand;
+            }
+            gsync();
+            int p = k, slot = 0;
+            if constexpr (kSearch) {
+                if constexpr (WPM > 1) {
+                    const PivotCand* pp = part + (k & 1) * WPM;
+                    PivotCand best = pp[0];
+#pragma unroll
+                    for (int w = 1; w < WPM; w++) {
+                        const PivotCand o = pp[w];
+                        const bool take = (o.v > best.v || (o.v == best.v && o.i < best.i));
+                        best = take ? o : best;
+                        slot = take ? w : slot;
+                    }
+                    p = best.i;
+                } else {
+                    p = cand.i;
                 }
-                p = cand.i;
             }
             if (r == 0) sP[k] = p;
             if (pos == p) pos = k;
             else if (pos == k) pos = p;
-            float* urow = sRow + (k & 1) * N;
-            if (pos == k) {  // this lane holds the pivot row: publish columns >= k and store row k of U
-                float4* ug4 = reinterpret_cast<float4*>(ug + k * N);
-                float4* ur4 = reinterpret_cast<float4*>(urow);
-#pragma unroll
-                for (int q = 0; q < N / 4; q++) {
-                    const float4 v = make_float4(4 * q >= k ? a[4 * q] : 0.0f, 4 * q + 1 >= k ? a[4 * q + 1] : 0.0f,
-                                                 4 * q + 2 >= k ? a[4 * q + 2] : 0.0f, 4 * q + 3 >= k ? a[4 * q + 3] : 0.0f);
-                    if (4 * q + 3 >= k) ur4[q] = v;
-                    __stcs(ug4 + q, v);
-                }
-            }
-            gsync();
+            const float* urow = slots + slot * N;
+            if (live) __stcs(ug + k * N + r, r >= k ? urow[r] : 0.0f);  // row k of U, one element per thread, coalesced
             if constexpr (k < N - 1) {
                 const float4* ur4 = reinterpret_cast<const float4*>(urow);
                 const float piv = urow[k];
@@ -445,7 +467,7 @@ lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
                 // (a value on the fast division path) and are updated along with the live ones
                 const bool act = pos > k;
                 const float lm = xdiv(act ? a[k] : piv, make_divisor(piv));
-                if (act) sA[pos * N + k] = lm;
+                if (act) sA[pos * LD + k] = lm;
                 constexpr int q1 = (k + 1) / 4;  // the quad of column k+1 first: the next search only needs that column
                 {
                     const float4 u = ur4[q1];
@@ -466,10 +488,17 @@ lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
             }
         });
         fence_async_smem();
-        gsync();
-        bulk_s2g(L + b * (long)(N * N) + r * N, sA + r * N, kRowBytes);
-        if (r == 0) bulk_s2g(P + b * (long)N, sP, N * 4);
-        bulk_commit();
+        gsync();  // every multiplier is in the slab, P is complete
+        if (live) {
+            if (r == 0) {
+                bulk_s2g(P + b * (long)N, sP, N * 4);
+                bulk_commit();
+            }
+            // L, row by row: thread r supplies column r (multiplier below the diagonal, 1 on it, 0 above)
+            float* lg = L + b * (long)(N * N) + r;
+#pragma unroll 8
+            for (int i = 0; i < N; i++) __stcs(lg + i * N, r < i ? sA[i * LD + r] : (r == i ? 1.0f : 0.0f));
+        }
     }
     bulk_wait_read<0>();
 }
@@ -621,14 +650,18 @@ static cudaError_t launch_lu_regs(const float* A, float* L, float* U, int* P, lo
 
 template <int N, bool FUSED>
 static cudaError_t launch_lu_lane(const float* A, float* L, float* U, int* P, long batch, int pivoting, cudaStream_t st) {
-    constexpr size_t per_mat = (size_t)((N * N + 4) + 2 * N + N + 8) * 4;
+    constexpr int WPM = N / 32;
+    constexpr size_t per_mat = (size_t)(N * (N + 1) + 2 * WPM * N + N + 4 * WPM) * 4;
     constexpr int fit = (int)((227 * 1024 - 1024) / (per_mat + 8));
     // registers bound the residency before shared memory does: a row of N floats per lane plus ~38 more
     // (N = 64: 10 matrices per CTA; measured 9 / 10 / 12 matrices: 16.6 / 17.7 / 17.0 M fact/s)
     constexpr int by_regs = 65536 / ((N + 38) * N);
     constexpr int MATS = fit * N > 1024 ? 1024 / N : (fit < by_regs ? fit : by_regs);
+    static_assert(MATS >= 1 && (WPM == 1 || MATS <= 15), "named barrier ids 1..15");
     const size_t smem = MATS * per_mat + MATS * sizeof(uint64_t);
     auto kern = pivoting ? lu_lane_kernel<N, MATS, true, FUSED> : lu_lane_kernel<N, MATS, false, FUSED>;
+    // (LOCKSTEP measured -18 % at N = 64 and -1 % at N = 128: the per-matrix barrier stays)
+    if (N >= 64 && pivoting && option(HLSD_OPT_LOCKSTEP) == 1) kern = lu_lane_kernel<N, MATS, true, FUSED, (N >= 64)>;
     cudaError_t e = ensure_dynamic_smem(kern, smem);
     if (e != cudaSuccess) return e;
     long grid = std::min<long>((batch + MATS - 1) / MATS, (long)sm_count());
@@ -660,8 +693,13 @@ static cudaError_t lu_dispatch(const float* A, float* L, float* U, int* P, int n
         if (aligned && n == 4) return launch_lu_tpm<4, FUSED>(A, L, U, P, batch, pivoting, st);
         if (aligned && n == 8) return launch_lu_regs<8, 2, 20, FUSED>(A, L, U, P, batch, pivoting, st);
         if (aligned && n == 16) return launch_lu_regs<16, 4, 12, FUSED, true>(A, L, U, P, batch, pivoting, st);  // U rows straight out: +10 %
-        if (aligned && n == 32) return launch_lu_regs<32, 16, 10, FUSED>(A, L, U, P, batch, pivoting, st);  // (lane kernel: 97 M vs 121 M fact/s)
+        if (aligned && n == 32) {
+            // measured (round 2, batch 259441): lane-per-row kernel 148 M fact/s, rows-in-registers kernel 116 M
+            if (option(HLSD_OPT_LU32_KERNEL) == 1) return launch_lu_regs<32, 16, 10, FUSED>(A, L, U, P, batch, pivoting, st);
+            return launch_lu_lane<32, FUSED>(A, L, U, P, batch, pivoting, st);
+        }
         if (aligned && n == 64) return launch_lu_lane<64, FUSED>(A, L, U, P, batch, pivoting, st);
+        if (aligned && n == 128) return launch_lu_lane<128, FUSED>(A, L, U, P, batch, pivoting, st);
         if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
     }
     const size_t per = (size_t)n * (n | 1) * 4;

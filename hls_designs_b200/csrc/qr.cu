@@ -264,7 +264,7 @@ qr_cols_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
 // (c, s) is broadcast by shuffle and applied by all lanes of the group to their columns of R to the right
 // of c and to their rows of Q.  Per-element operation order is the sequential loop's: bit-identical.
 // ------------------------------------------------------------------------------------------------
-template <int N, int K, int WARPS, bool FUSED>
+template <int N, int K, int WARPS, bool FUSED, bool LOCKSTEP = false>  // LOCKSTEP: see chol_rows_kernel (chol.cu)
 __global__ void __launch_bounds__(WARPS * 32, 1)
 qr_wcols_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restrict__ R, long batch) {
     constexpr int C = N / K;     // lanes per matrix
@@ -286,9 +286,11 @@ qr_wcols_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __res
     __syncwarp();
     const long num_slabs = (batch + MPW - 1) / MPW;
     uint32_t parity = 0;
-    for (long sl = (long)blockIdx.x * WARPS + warp; sl < num_slabs; sl += (long)gridDim.x * WARPS) {
+    for (long sl0 = (long)blockIdx.x * WARPS; sl0 < num_slabs; sl0 += (long)gridDim.x * WARPS) {
+        const long sl = sl0 + warp;
+        if (!LOCKSTEP && sl >= num_slabs) break;
         const long m0 = sl * MPW;
-        const int valid = (int)min((long)MPW, batch - m0);
+        const int valid = sl < num_slabs ? (int)min((long)MPW, batch - m0) : 0;
         bulk_wait_read<0>();
         __syncwarp();
         if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * kMatBytes);
@@ -310,6 +312,7 @@ qr_wcols_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __res
             constexpr int c_lo = (s - N + 2) > 0 ? (s - N + 2) : 0;
             constexpr int c_hi = (s / 2) < (N - 2) ? (s / 2) : (N - 2);
             constexpr int nrot = c_hi - c_lo + 1;
+            if constexpr (LOCKSTEP && nrot > 0) __syncthreads();
             if constexpr (nrot > 0) {
                 static_for<0, (nrot + C - 1) / C>([&](auto chc) {
                     constexpr int cb = c_lo + decltype(chc)::value * C;
@@ -716,7 +719,10 @@ template <int N, int K, int WARPS, bool FUSED>
 static cudaError_t launch_qr_wcols(const float* A, float* Q, float* R, long batch, cudaStream_t st) {
     constexpr int MPW = 32 / (N / K);
     const size_t smem = (size_t)WARPS * MPW * 2 * (N * N + 4) * 4 + WARPS * sizeof(uint64_t);
-    auto kern = qr_wcols_kernel<N, K, WARPS, FUSED>;
+    // one CTA-wide barrier per wave step (LOCKSTEP) measured +8 % at 32x32 (43.0 M -> 46.7 M fact/s), +1 % at 16x16
+    constexpr bool kLock = N == 32;
+    auto kern = qr_wcols_kernel<N, K, WARPS, FUSED, kLock>;
+    if (N >= 16 && option(HLSD_OPT_LOCKSTEP) == 1) kern = qr_wcols_kernel<N, K, WARPS, FUSED, (N >= 16 && !kLock)>;
     cudaError_t e = ensure_dynamic_smem(kern, smem);
     if (e != cudaSuccess) return e;
     const long num_slabs = (batch + MPW - 1) / MPW;

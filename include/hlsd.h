@@ -132,6 +132,19 @@ int64_t hlsd_launch_count(void);           /* kernels launched by this library s
 const char* hlsd_last_error(void);         /* thread-local, never NULL */
 const char* hlsd_version(void);
 
+/* ---- measurement switches (diagnostic).  Where two kernels serve the same request, the library runs the one
+ * that measured faster on B200; these switches select the other one so that the choice can be re-measured
+ * (scripts/ab_*.py).  Every setting computes the same results (bit-identical on the exact paths).  Process-wide;
+ * returns HLSD_ERR_INVALID for an unknown option. */
+#define HLSD_OPT_CHOL_SLAB 1    /* Cholesky register kernels: 0 = default (N = 32 dense slab, N = 64 packed lower-triangle
+                                   slab), 1 = the other layout, 2 = N = 32 packed with 8 warps per SM                */
+#define HLSD_OPT_LU32_KERNEL 2  /* LU 32x32: 0 = lane-per-row kernel (default), 1 = rows-in-registers kernel          */
+#define HLSD_OPT_DIAG_KERNEL 3  /* tensor paths, 128x128 diagonal block: 0 = default, 1 = the other implementation   */
+#define HLSD_OPT_LOCKSTEP 4     /* unrolled register kernels (Cholesky 32/64, LU 64/128, QR 16/32): 0 = default, 1 = the other
+                                   of {free-running warps, one CTA-wide barrier per step}                             */
+#define HLSD_OPT_COUNT 8
+int hlsd_set_option(int option, int value);
+
 /* ---- per-kernel-class timing of the blocked paths (diagnostic; used by bench.py for the roofline of the dominant
  * kernel).  Between hlsd_profile_begin() and hlsd_profile_end() every kernel launch of the library is bracketed by
  * CUDA events on its stream; hlsd_profile_end() waits for them and ADDS the elapsed milliseconds per class to

@@ -25,6 +25,38 @@ KEEP = [
 STALL = "smsp__average_warps_issue_stalled_"
 
 
+def instruction_mix(rep):
+    """Per SASS opcode: warp instructions executed and stall samples (ncu --page source), top 18 by samples."""
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr = None
+    mix = {}
+    for r in rows:
+        if r and r[0] == "Address":
+            hdr = r
+            continue
+        if not hdr or len(r) < len(hdr) - 2 or not r[0].startswith("0x"):
+            continue
+        d = dict(zip(hdr, r))
+        toks = d["Source"].split()
+        if toks and toks[0].startswith("@"):
+            toks = toks[1:]
+        op = toks[0].split(".")[0] if toks else "?"
+        try:
+            n, smp = int(d["Instructions Executed"]), int(d["# Samples"])
+        except (KeyError, ValueError):
+            continue
+        e = mix.setdefault(op, [0, 0])
+        e[0] += n
+        e[1] += smp
+    tot_n = sum(v[0] for v in mix.values()) or 1
+    tot_s = sum(v[1] for v in mix.values()) or 1
+    print(f"# instruction mix (SASS opcode: share of warp instructions executed, share of stall samples); {tot_n} instructions, {tot_s} samples")
+    for op, (n, smp) in sorted(mix.items(), key=lambda kv: -kv[1][1])[:18]:
+        print(f"  {op:12s} {100.0 * n / tot_n:6.2f} % of instructions   {100.0 * smp / tot_s:6.2f} % of samples")
+    print()
+
+
 def main():
     rep, how = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "")
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
@@ -43,6 +75,7 @@ def main():
         for v, k in stalls[:8]:
             print(f"{k:90s} {v:20.4f} warps per issue")
         print()
+    instruction_mix(rep)
 
 
 if __name__ == "__main__":

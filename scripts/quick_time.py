@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Time one decomposition at one size on the GPU (operands resident in HBM, CUDA events, median of 5).
-Usage: python scripts/quick_time.py <chol|lu|qr> <n> [batch]"""
+Usage: python scripts/quick_time.py <chol|lu|qr> <n> [batch] [--fused] [--opt name=value ...]"""
 import os
 import statistics
 import sys
@@ -12,9 +12,15 @@ sys.path.insert(0, ROOT)
 import hls_designs_b200 as hd  # noqa: E402
 from bench import algorithmic_bytes  # noqa: E402
 
-kind, n = sys.argv[1], int(sys.argv[2])
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+fused = "--fused" in sys.argv
+opts = [a for i, a in enumerate(sys.argv) if i > 0 and sys.argv[i - 1] == "--opt"]
+argv = [a for a in argv if a not in opts]
+for o in opts:
+    hd.set_option(o.split("=")[0], int(o.split("=")[1]))
+kind, n = argv[0], int(argv[1])
 per = algorithmic_bytes(kind, n, n)
-batch = int(sys.argv[3]) if len(sys.argv) > 3 else int(max(64, min(1 << 20, (3 << 30) // per)))
+batch = int(argv[2]) if len(argv) > 2 else int(max(64, min(1 << 20, (3 << 30) // per)))
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev).manual_seed(7)
 if kind == "chol":
@@ -22,10 +28,16 @@ if kind == "chol":
     A = (0.5 * (A + A.transpose(1, 2)))
     A.diagonal(dim1=1, dim2=2).add_(float(n))
     A = A.contiguous()
-    fn = hd.cholesky
+    fn0 = hd.cholesky
 else:
     A = torch.randint(1, 101, (batch, n, n), generator=g, device=dev).float()
-    fn = hd.lu if kind == "lu" else hd.qr
+    fn0 = hd.lu if kind == "lu" else hd.qr
+
+
+def fn(x):
+    return fn0(x, fused=fused)
+
+
 for _ in range(3):
     fn(A)
 torch.cuda.synchronize()
@@ -38,5 +50,5 @@ for _ in range(5):
     torch.cuda.synchronize()
     ms.append(s.elapsed_time(e))
 t = statistics.median(ms) * 1e-3
-print(f"{kind} n={n} batch={batch} env={ {k: v for k, v in os.environ.items() if k.startswith('HLSD_')} }: "
+print(f"{kind} n={n} batch={batch} fused={fused} opts={opts}: "
       f"{t * 1e3:.3f} ms  {batch / t:.4g} fact/s  {per * batch / t / 1e9:.0f} GB/s")
