@@ -273,6 +273,256 @@ blk_diag_kernel(const float* __restrict__ S, float* __restrict__ L, float* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// Diagonal block, blocked (round 2).  ncu on blk_diag_kernel above: one barrier per column and a 4 x 8 register tile
+// per thread mean ~2000 warp instructions per column for ~256 warp FMAs of useful work (issue slots 55 % busy, 13 %
+// of them FMAs).  Here the 128 x 128 block is factored by 32-column sub-blocks, so that the per-column cost is paid
+// on 32 x 32 blocks inside ONE warp (rows in registers, shuffles, no barrier) and everything else is a dot product
+// over contiguous k with 2 x 2 register tiles (4 float4 loads per 16 FMAs):
+//   for j = 0..3:  (a) block column j -= L[:, :32j] L[32j.., :32j]^T                (left-looking, K = 32 j)
+//                  (b) warp 0: L_jj = chol(diagonal block), D_j = inv(L_jj)          (lane = row, then lane = column)
+//                  (c) rows below: L[:, j] = X[:, j] D_j^T                             (thread = row)
+//   for r = 1..3:  S = L[r, :r] W[:r, :r];  W[r, :r] = -D_r S                         (block row r of W = inv(L11))
+// W[i][j] (i >= j) lives TRANSPOSED in the unused upper triangle of the same tile, at tile[j][i + 4]: both factors
+// of every product are then contiguous in k.  256 threads, 100 KB of shared memory, two CTAs per SM.
+// INV_ONLY (blocked LU): the block is a finished unit-lower L11; warps 0..3 invert the four diagonal blocks, then
+// the block rows of W follow as above.  Plain fp32 FMA arithmetic (tensor paths: tolerance-checked).
+// ------------------------------------------------------------------------------------------------
+struct Diag2 {
+    static constexpr int LDT = 132;  // row stride of the tile: rows stay 16-byte aligned, W^T fits with its shift
+    static constexpr int SH = 4;     // W[i][j] is kept at tile[j][i + SH]
+    static constexpr int LDN = 36;   // row stride of the inverted diagonal blocks (natural layout) and of the scratch
+    static constexpr int kTile = NB * LDT, kDn = 4 * 32 * LDN, kSt = 96 * LDN;
+    static constexpr int kBytes = (kTile + kDn + kSt) * 4;
+};
+
+__device__ __forceinline__ float dot4(float4 a, float4 b, float s) {
+    s = fmaf(a.x, b.x, s);
+    s = fmaf(a.y, b.y, s);
+    s = fmaf(a.z, b.z, s);
+    return fmaf(a.w, b.w, s);
+}
+
+// One warp: Cholesky of the 32 x 32 diagonal block at (c0, c0) of the tile.  lane = row; the row lives in registers,
+// the pivot and the column stream travel by shuffle.  L_jj goes back into the tile (lower part only: W^T lives above
+// it), 1 / l_kk into rd[0..31].  This is the serial part of the kernel (four times 32 dependent pivot steps), so it
+// holds nothing else in registers: the inverse of the block is taken later, by other warps (inv32).
+__device__ __forceinline__ void chol32(float* T, float* rd, int c0, int lane) {
+    constexpr int LDT = Diag2::LDT;
+    float d[32];
+    {
+        const float4* row4 = reinterpret_cast<const float4*>(T + (c0 + lane) * LDT + c0);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const float4 v = row4[q];
+            d[4 * q] = v.x, d[4 * q + 1] = v.y, d[4 * q + 2] = v.z, d[4 * q + 3] = v.w;
+        }
+    }
+    static_for<0, 32>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        const float pk = __shfl_sync(0xffffffffu, d[k], k);
+        const float rk = rsqrtf(pk);  // 2 ulp: far inside the tolerance of the tensor path
+        if (lane == k) rd[k] = rk;
+        const float lk = d[k] * rk;   // l_ik for rows i > k, sqrt(a_kk) in lane k
+        d[k] = lk;
+#pragma unroll
+        for (int c = k + 1; c < 32; c++) d[c] = fmaf(-lk, __shfl_sync(0xffffffffu, lk, c), d[c]);
+    });
+#pragma unroll
+    for (int c = 0; c < 32; c++)
+        if (c <= lane) T[(c0 + lane) * LDT + c0 + c] = d[c];
+}
+
+// One warp: D = inv(L_jj) of the 32 x 32 lower-triangular block at (c0, c0) of the tile; lane = column of D:
+// x_i = (delta_i,lane - sum_{k<i} l_ik x_k) * rd_i, rows of L_jj read as broadcast float4 loads.  D goes to Dn (natural
+// layout, zeros above the diagonal) and, transposed, into the upper triangle of the tile (W_jj).
+__device__ __forceinline__ void inv32(float* T, float* Dn, const float* rd, int c0, int lane) {
+    constexpr int LDT = Diag2::LDT, LDN = Diag2::LDN, SH = Diag2::SH;
+    float x[32];
+    static_for<0, 32>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        float a0 = (i == lane) ? 1.0f : 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        const float4* lrow = reinterpret_cast<const float4*>(T + (c0 + i) * LDT + c0);
+        static_for<0, (i + 3) / 4>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            const float4 lv = lrow[q];
+            if constexpr (4 * q < i) a0 = fmaf(-lv.x, x[4 * q], a0);
+            if constexpr (4 * q + 1 < i) a1 = fmaf(-lv.y, x[4 * q + 1], a1);
+            if constexpr (4 * q + 2 < i) a2 = fmaf(-lv.z, x[4 * q + 2], a2);
+            if constexpr (4 * q + 3 < i) a3 = fmaf(-lv.w, x[4 * q + 3], a3);
+        });
+        x[i] = ((a0 + a1) + (a2 + a3)) * rd[i];
+    });
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        Dn[i * LDN + lane] = x[i];                                  // (x_i = 0 for i < lane)
+        if (i >= lane) T[(c0 + lane) * LDT + c0 + i + SH] = x[i];  // W_jj, transposed into the upper triangle
+    }
+}
+
+template <bool INV_ONLY>
+__global__ void __launch_bounds__(256, 2)
+blk_diag2_kernel(const float* __restrict__ S, float* __restrict__ L, float* __restrict__ W, int n, int o) {
+    constexpr int LDT = Diag2::LDT, LDN = Diag2::LDN, SH = Diag2::SH;
+    extern __shared__ __align__(16) float d2_smem[];
+    float* T = d2_smem;
+    float* Dn = T + Diag2::kTile;  // [4][32][LDN]
+    float* St = Dn + Diag2::kDn;   // [96][LDN]: S transposed (column-major), S[i][c] at St[c][i]
+    __shared__ float rdiag[NB];    // 1 / l_kk (1 for the unit-lower block of the LU)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* sblk = S + (long)blockIdx.x * n * n + (long)o * n + o;  // S = A for block column 0, L afterwards
+    float* blk = L + (long)blockIdx.x * n * n + (long)o * n + o;
+    for (int e = tid; e < NB * (NB / 4); e += 256) {
+        const int row = e >> 5, c4 = e & 31;
+        *reinterpret_cast<float4*>(T + row * LDT + 4 * c4) = *(reinterpret_cast<const float4*>(sblk + (long)row * n) + c4);
+    }
+    if (INV_ONLY && tid < NB) rdiag[tid] = 1.0f;
+    __syncthreads();
+    if constexpr (!INV_ONLY) {
+        for (int j = 0; j < 4; j++) {
+            const int c0 = 32 * j;
+            if (j > 0) {
+                // (a) left-looking update of block column j: 2 x 2 tiles (rows r0, r0+1; columns ca, ca+16), K = c0
+                const int tiles = ((NB - c0) / 2) * 16;
+                for (int t = tid; t < tiles; t += 256) {
+                    const int cp = t & 15, rp = t >> 4;
+                    const int r0 = c0 + 2 * rp, ca = c0 + cp, cb = ca + 16;
+                    if (r0 + 1 < ca) continue;  // entirely above the diagonal
+                    const float4* A0 = reinterpret_cast<const float4*>(T + r0 * LDT);
+                    const float4* A1 = reinterpret_cast<const float4*>(T + (r0 + 1) * LDT);
+                    const float4* B0 = reinterpret_cast<const float4*>(T + ca * LDT);
+                    const float4* B1 = reinterpret_cast<const float4*>(T + cb * LDT);
+                    float s00 = 0.0f, s01 = 0.0f, s10 = 0.0f, s11 = 0.0f;
+                    for (int k4 = 0; k4 < c0 / 4; k4++) {
+                        const float4 a0 = A0[k4], a1 = A1[k4], b0 = B0[k4], b1 = B1[k4];
+                        s00 = dot4(a0, b0, s00), s01 = dot4(a0, b1, s01);
+                        s10 = dot4(a1, b0, s10), s11 = dot4(a1, b1, s11);
+                    }
+                    if (r0 >= ca) T[r0 * LDT + ca] -= s00;
+                    if (r0 >= cb) T[r0 * LDT + cb] -= s01;
+                    if (r0 + 1 >= ca) T[(r0 + 1) * LDT + ca] -= s10;
+                    if (r0 + 1 >= cb) T[(r0 + 1) * LDT + cb] -= s11;
+                }
+                __syncthreads();
+            }
+            // (b) the 32 x 32 diagonal block: Cholesky inside warp 0 (the serial part).  Meanwhile the other seven warps
+            //     write a quarter of the zeros this block row of L needs right of its diagonal block (nothing else ever
+            //     writes those blocks; the stores are fire-and-forget and cost the factorisation nothing)
+            if (warp == 0) {
+                chol32(T, rdiag + c0, c0, lane);
+            } else {
+                const int zcols4 = (n - o - NB) / 4;  // float4 per row right of the diagonal block
+                float4* zbase = reinterpret_cast<float4*>(blk + NB);
+                for (int row = c0; row < c0 + 32; row++)
+                    for (int c4 = tid - 32; c4 < zcols4; c4 += 224)
+                        __stcs(zbase + (long)row * (n / 4) + c4, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+            }
+            __syncthreads();
+            // (c) rows below the diagonal block, thread = row, forward substitution against L_jj (read as broadcast
+            //     float4 loads): l_rc = (x_c - sum_{m<c} l_rm l_cm) / l_cc
+            if (tid < NB - c0 - 32) {
+                float* xrow = T + (c0 + 32 + tid) * LDT + c0;
+                float xr[32];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const float4 v = reinterpret_cast<const float4*>(xrow)[q];
+                    xr[4 * q] = v.x, xr[4 * q + 1] = v.y, xr[4 * q + 2] = v.z, xr[4 * q + 3] = v.w;
+                }
+                static_for<0, 32>([&](auto cc) {
+                    constexpr int c = decltype(cc)::value;
+                    float a0 = xr[c], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                    const float4* lrow = reinterpret_cast<const float4*>(T + (c0 + c) * LDT + c0);
+                    static_for<0, (c + 3) / 4>([&](auto qc) {
+                        constexpr int q = decltype(qc)::value;
+                        const float4 lv = lrow[q];
+                        if constexpr (4 * q < c) a0 = fmaf(-lv.x, xr[4 * q], a0);
+                        if constexpr (4 * q + 1 < c) a1 = fmaf(-lv.y, xr[4 * q + 1], a1);
+                        if constexpr (4 * q + 2 < c) a2 = fmaf(-lv.z, xr[4 * q + 2], a2);
+                        if constexpr (4 * q + 3 < c) a3 = fmaf(-lv.w, xr[4 * q + 3], a3);
+                    });
+                    xr[c] = ((a0 + a1) + (a2 + a3)) * rdiag[c0 + c];
+                });
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    reinterpret_cast<float4*>(xrow)[q] = make_float4(xr[4 * q], xr[4 * q + 1], xr[4 * q + 2], xr[4 * q + 3]);
+            }
+            __syncthreads();
+        }
+    }
+    // D_j = inv(L_jj) for the four diagonal blocks, one warp each (off the serial path: nothing above needed them)
+    if (warp >= 4) inv32(T, Dn + (warp - 4) * 32 * LDN, rdiag + 32 * (warp - 4), 32 * (warp - 4), lane);
+    __syncthreads();
+    // block rows 1..3 of W = inv(L11)
+    for (int r = 1; r < 4; r++) {
+        const int r0 = 32 * r;
+        // S[i][c] = sum_{k = c}^{r0 - 1} L[r0 + i][k] W[k][c]: tiles (rows ia, ia + 16) x (columns ca, ca + 1)
+        for (int t = tid; t < 16 * (r0 / 2); t += 256) {
+            const int ip = t & 15, cp = t >> 4;
+            const int ca = 2 * cp, ia = ip, ib = ip + 16;
+            const float4* A0 = reinterpret_cast<const float4*>(T + (r0 + ia) * LDT);
+            const float4* A1 = reinterpret_cast<const float4*>(T + (r0 + ib) * LDT);
+            const float4* B0 = reinterpret_cast<const float4*>(T + ca * LDT + SH);        // W[k][ca] at k
+            const float4* B1 = reinterpret_cast<const float4*>(T + (ca + 1) * LDT + SH);  // W[k][ca + 1]
+            float s00 = 0.0f, s01 = 0.0f, s10 = 0.0f, s11 = 0.0f;
+            const int kfirst = ca >> 2;
+            for (int k4 = kfirst; k4 < r0 / 4; k4++) {
+                const float4 a0 = A0[k4], a1 = A1[k4];
+                float4 b0 = B0[k4], b1 = B1[k4];
+                if (k4 == kfirst) {  // W[k][c] = 0 for k < c: what sits there in the tile is L
+                    const int k = 4 * k4;
+                    if (k < ca) b0.x = 0.0f;
+                    if (k + 1 < ca) b0.y = 0.0f;
+                    if (k + 2 < ca) b0.z = 0.0f;
+                    if (k < ca + 1) b1.x = 0.0f;
+                    if (k + 1 < ca + 1) b1.y = 0.0f;
+                    if (k + 2 < ca + 1) b1.z = 0.0f;
+                    if (k + 3 < ca + 1) b1.w = 0.0f;
+                }
+                s00 = dot4(a0, b0, s00), s01 = dot4(a0, b1, s01);
+                s10 = dot4(a1, b0, s10), s11 = dot4(a1, b1, s11);
+            }
+            St[ca * LDN + ia] = s00, St[(ca + 1) * LDN + ia] = s01;
+            St[ca * LDN + ib] = s10, St[(ca + 1) * LDN + ib] = s11;
+        }
+        __syncthreads();
+        // W[r0 + i][c] = -sum_{m <= i} D_r[i][m] S[m][c]
+        const float* dn = Dn + r * 32 * LDN;
+        for (int t = tid; t < 16 * (r0 / 2); t += 256) {
+            const int ip = t & 15, cp = t >> 4;
+            const int ca = 2 * cp, ia = ip, ib = ip + 16;
+            const float4* D0 = reinterpret_cast<const float4*>(dn + ia * LDN);
+            const float4* D1 = reinterpret_cast<const float4*>(dn + ib * LDN);
+            const float4* S0 = reinterpret_cast<const float4*>(St + ca * LDN);
+            const float4* S1 = reinterpret_cast<const float4*>(St + (ca + 1) * LDN);
+            float s00 = 0.0f, s01 = 0.0f, s10 = 0.0f, s11 = 0.0f;
+            for (int m4 = 0; m4 <= (ib >> 2); m4++) {  // D_r[i][m] = 0 for m > i (stored)
+                const float4 d0 = D0[m4], d1 = D1[m4], v0 = S0[m4], v1 = S1[m4];
+                s00 = dot4(d0, v0, s00), s01 = dot4(d0, v1, s01);
+                s10 = dot4(d1, v0, s10), s11 = dot4(d1, v1, s11);
+            }
+            T[ca * LDT + r0 + ia + SH] = -s00, T[(ca + 1) * LDT + r0 + ia + SH] = -s01;
+            T[ca * LDT + r0 + ib + SH] = -s10, T[(ca + 1) * LDT + r0 + ib + SH] = -s11;
+        }
+        __syncthreads();
+    }
+    if constexpr (!INV_ONLY) {
+        for (int e = tid; e < NB * (NB / 4); e += 256) {
+            const int row = e >> 5, c4 = e & 31;
+            float4 v = *reinterpret_cast<const float4*>(T + row * LDT + 4 * c4);
+            if (4 * c4 > row) v.x = 0.0f;
+            if (4 * c4 + 1 > row) v.y = 0.0f;
+            if (4 * c4 + 2 > row) v.z = 0.0f;
+            if (4 * c4 + 3 > row) v.w = 0.0f;
+            *(reinterpret_cast<float4*>(blk + (long)row * n) + c4) = v;
+        }
+    }
+    float* wout = W + (long)blockIdx.x * NB * NB;
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int i = e >> 7, j = e & (NB - 1);
+        wout[e] = (j <= i) ? T[j * LDT + i + SH] : 0.0f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // tensor-core tile kernel
 // ------------------------------------------------------------------------------------------------
 struct MmaSmem {
@@ -610,9 +860,11 @@ static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int
     if ((e = ensure_dynamic_smem(blk_mma_kernel, MmaSmem::kTotal)) != cudaSuccess) return e;
     if ((e = ensure_dynamic_smem(blk_ll2_kernel, Ll2Smem::kTotal)) != cudaSuccess) return e;
     if ((e = ensure_dynamic_smem(blk_diag_kernel<DIAG_CHOL_INV>, kDiagSmem)) != cudaSuccess) return e;
+    if ((e = ensure_dynamic_smem(blk_diag2_kernel<false>, Diag2::kBytes)) != cudaSuccess) return e;
+    const bool old_diag = option(HLSD_OPT_DIAG_KERNEL) == 1;  // the round-1 column-by-column kernel (A/B measurements)
     const int panels = n / NB;
     const unsigned nb = (unsigned)batch;
-    {
+    if (old_diag) {  // (blk_diag2_kernel writes the zero blocks of its block row itself)
         ProfScope ps(HLSD_PROF_OTHER, st);
         blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, nb), 256, 0, st>>>(L, n);
         count_launch();
@@ -630,7 +882,8 @@ static cudaError_t cholesky_left_looking(const float* A, float* L, float* W, int
         }
         {
             ProfScope ps(HLSD_PROF_DIAG, st);
-            blk_diag_kernel<DIAG_CHOL_INV><<<nb, 512, kDiagSmem, st>>>(src, L, W, n, o);
+            if (old_diag) blk_diag_kernel<DIAG_CHOL_INV><<<nb, 512, kDiagSmem, st>>>(src, L, W, n, o);
+            else blk_diag2_kernel<false><<<nb, 256, Diag2::kBytes, st>>>(src, L, W, n, o);
             count_launch();
         }
         if (mt > 0) {
@@ -1125,6 +1378,8 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
     const size_t unswap_smem = (size_t)2 * NB * (NB + 1) * sizeof(float) + (size_t)n * sizeof(int);
     if ((e = ensure_dynamic_smem(lu_unswap_panel_kernel, unswap_smem)) != cudaSuccess) return e;
     if ((e = ensure_dynamic_smem(blk_diag_kernel<DIAG_INV_ONLY>, kDiagSmem)) != cudaSuccess) return e;
+    if ((e = ensure_dynamic_smem(blk_diag2_kernel<true>, Diag2::kBytes)) != cudaSuccess) return e;
+    const bool old_diag = option(HLSD_OPT_DIAG_KERNEL) == 1;
     if ((e = ensure_dynamic_smem(gemm_tile_kernel<0>, MmaSmem::kTotal)) != cudaSuccess) return e;
     if ((e = ensure_dynamic_smem(gemm_tile_kernel<1>, MmaSmem::kTotal)) != cudaSuccess) return e;
     // one workspace: W = inv(L11) per matrix, T0 = A12^T, T1 = U12^T
@@ -1172,7 +1427,8 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
         }
         {
             ProfScope ps(HLSD_PROF_DIAG, st);
-            blk_diag_kernel<DIAG_INV_ONLY><<<nb, 512, kDiagSmem, st>>>(L, L, Winv, n, o);  // W = inv(L11), L11 unit lower
+            if (old_diag) blk_diag_kernel<DIAG_INV_ONLY><<<nb, 512, kDiagSmem, st>>>(L, L, Winv, n, o);  // W = inv(L11), L11 unit lower
+            else blk_diag2_kernel<true><<<nb, 256, Diag2::kBytes, st>>>(L, L, Winv, n, o);
             count_launch();
         }
         {
