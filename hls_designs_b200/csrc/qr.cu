@@ -524,9 +524,15 @@ qr_wave_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
 // offset from a per-step base pointer.  Per rotation and Q row: one 8-byte shared-memory load and the six
 // floating-point operations, instead of two loads, two stores and address arithmetic on top.
 // ------------------------------------------------------------------------------------------------
-template <int N, int RT, bool FUSED>
-__global__ void __launch_bounds__(RT + N, N == 64 ? 4 : 1)
+// UNI: ONE set of N threads per matrix does both jobs (thread t: the R work of R-thread t, then row t of Q), which
+// halves the threads and registers a matrix occupies: two (128 x 128) or more CTAs share an SM, and one matrix's
+// angle generation and barrier waits are filled by another matrix's rotations.  (ncu on the two-role kernel at
+// 128 x 128, one CTA per SM: issue slots 45 % busy, `barrier` + `wait` the top stalls.)
+template <int N, int RT, bool FUSED, bool UNI = false>
+__global__ void __launch_bounds__(UNI ? N : RT + N, UNI ? (N == 64 ? 8 : 2) : (N == 64 ? 4 : 1))
 qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restrict__ R, long batch) {
+    static_assert(!UNI || RT == N, "unified threads: one thread per R column group and Q row");
+    constexpr int NT = UNI ? N : RT + N;  // threads per CTA
     extern __shared__ __align__(16) float smem_f[];
     constexpr int ldr = N | 1;
     float* r = smem_f;                                   // N x ldr
@@ -534,13 +540,15 @@ qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
     // unconditionally and discard); N * ldr is even, so the buffer is 8-byte aligned
     float2* cs2 = reinterpret_cast<float2*>(r + N * ldr) + 8;
     const int t = threadIdx.x;
-    const bool q_side = t >= RT;  // threads 0..RT-1 work on R, thread RT + j holds row j of Q
+    const bool q_side = UNI || t >= RT;  // threads 0..RT-1 work on R, thread RT + j (UNI: thread j) holds row j of Q
+    const bool r_side = UNI || t < RT;
+    const int qrow = UNI ? t : t - RT;
     for (long b = blockIdx.x; b < batch; b += gridDim.x) {
         const float* a = A + b * (long)(N * N);
-        for (int e = t; e < N * N; e += RT + N) r[(e / N) * ldr + (e % N)] = a[e];
+        for (int e = t; e < N * N; e += NT) r[(e / N) * ldr + (e % N)] = a[e];
         float qq[N];
 #pragma unroll
-        for (int i = 0; i < N; i++) qq[i] = (q_side && i == t - RT) ? 1.0f : 0.0f;
+        for (int i = 0; i < N; i++) qq[i] = (q_side && i == qrow) ? 1.0f : 0.0f;
         __syncthreads();
         constexpr int last_t = (N - 1) + 2 * (N - 1);
         for (int step = 0; step <= last_t; step++) {
@@ -549,7 +557,7 @@ qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
             const int nrot = c_hi - c_lo + 1;
             if (nrot <= 0) continue;
             const int i0 = N - 1 - step + 2 * c_lo;  // row index of rotation k: i0 + 2 k
-            if (!q_side) {
+            if (r_side) {
                 for (int k = t; k < nrot; k += RT) {
                     const int c = c_lo + k, i = i0 + 2 * k;
                     float lo = r[(i - 1) * ldr + c], hi = r[i * ldr + c];
@@ -561,7 +569,7 @@ qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
                 }
             }
             __syncthreads();
-            if (!q_side) {
+            if (r_side) {
                 // R: columns x = tx, tx + 32, ... take the rotations with c < x; rotations k = ty, ty + GY, ...
                 constexpr int GY = RT / 32;
                 const int tx = t & 31, ty = t >> 5;
@@ -607,7 +615,8 @@ qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
                         }
                     }
                 }
-            } else {
+            }
+            if (q_side) {
                 const int bb = N - 1 - step;  // hi row of rotation c: bb + 2 c
                 const int p0 = bb >> 1;       // floor(bb / 2): slot of rotation c is p0 + c
                 const int plo = p0 + c_lo, phi = p0 + c_hi;
@@ -649,9 +658,9 @@ qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
             __syncthreads();
         }
         float* ro = R + b * (long)(N * N);
-        for (int e = t; e < N * N; e += RT + N) ro[e] = r[(e / N) * ldr + (e % N)];
+        for (int e = t; e < N * N; e += NT) ro[e] = r[(e / N) * ldr + (e % N)];
         if (q_side) {
-            float4* q4 = reinterpret_cast<float4*>(Q + b * (long)(N * N) + (long)(t - RT) * N);
+            float4* q4 = reinterpret_cast<float4*>(Q + b * (long)(N * N) + (long)qrow * N);
 #pragma unroll
             for (int v = 0; v < N / 4; v++) q4[v] = make_float4(qq[4 * v], qq[4 * v + 1], qq[4 * v + 2], qq[4 * v + 3]);
         }
@@ -732,16 +741,17 @@ static cudaError_t launch_qr_wcols(const float* A, float* Q, float* R, long batc
     return cudaGetLastError();
 }
 
-template <int N, int RT, bool FUSED>
+template <int N, int RT, bool FUSED, bool UNI = false>
 static cudaError_t launch_qr_qreg(const float* A, float* Q, float* R, long batch, cudaStream_t st) {
     const size_t smem = ((size_t)N * (N | 1) + 2 * (N / 2 + 2 + 8 + 4 * (RT / 32))) * 4;  // slack behind cs: 3 * GY entries
-    auto kern = qr_qreg_kernel<N, RT, FUSED>;
+    auto kern = qr_qreg_kernel<N, RT, FUSED, UNI>;
+    constexpr int NT = UNI ? N : RT + N;
     cudaError_t e = ensure_dynamic_smem(kern, smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RT + N, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
     long grid = std::min<long>(batch, (long)sm_count() * std::max(1, per_sm));
-    kern<<<(unsigned)grid, RT + N, smem, st>>>(A, Q, R, batch);
+    kern<<<(unsigned)grid, NT, smem, st>>>(A, Q, R, batch);
     count_launch();
     return cudaGetLastError();
 }
@@ -789,6 +799,10 @@ static cudaError_t qr_dispatch(const float* A, float* Q, float* R, int rows, int
         if (path == HLSD_PATH_TPM) return cudaErrorInvalidValue;
     }
     if (VARIANT == 0 && aligned && rows == cols && path == HLSD_PATH_AUTO) {
+        // measured (round 2): one set of threads for R and Q (UNI) 6.22 M / 683 k fact/s at 64 / 128, separate R and Q
+        // threads 5.20 M / 541 k
+        if (rows == 64 && option(HLSD_OPT_QR_THREADS) != 1) return launch_qr_qreg<64, 64, FUSED, true>(A, Q, R, batch, st);
+        if (rows == 128 && option(HLSD_OPT_QR_THREADS) != 1) return launch_qr_qreg<128, 128, FUSED, true>(A, Q, R, batch, st);
         if (rows == 64) return launch_qr_qreg<64, 64, FUSED>(A, Q, R, batch, st);  // (128 R threads, 3 CTAs per SM: 4.0 M vs 5.2 M fact/s)
         // (256 R threads would halve the R side of a step, but 384 threads cap the kernel at 168 registers and the
         // 128-register Q rows spill: 217 k instead of 545 k fact/s)

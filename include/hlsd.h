@@ -142,6 +142,8 @@ const char* hlsd_version(void);
 #define HLSD_OPT_DIAG_KERNEL 3  /* tensor paths, 128x128 diagonal block: 0 = default, 1 = the other implementation   */
 #define HLSD_OPT_LOCKSTEP 4     /* unrolled register kernels (Cholesky 32/64, LU 64/128, QR 16/32): 0 = default, 1 = the other
                                    of {free-running warps, one CTA-wide barrier per step}                             */
+#define HLSD_OPT_QR_THREADS 5   /* QR 64x64 / 128x128: 0 = one set of threads does the R and the Q work (default),
+                                   1 = separate R and Q threads (round 1)                                            */
 #define HLSD_OPT_COUNT 8
 int hlsd_set_option(int option, int value);
 

@@ -33,8 +33,8 @@ CASES = {
     "qr8": ("qr", 8, [("default", {}, False)]),
     "qr16": ("qr", 16, [("default", {}, False), ("lockstep", {"lockstep": 1}, False), ("fused", {}, True)]),
     "qr32": ("qr", 32, [("default", {}, False), ("lockstep", {"lockstep": 1}, False), ("fused", {}, True)]),
-    "qr64": ("qr", 64, [("default", {}, False), ("fused", {}, True)]),
-    "qr128": ("qr", 128, [("default", {}, False), ("fused", {}, True)]),
+    "qr64": ("qr", 64, [("default", {}, False), ("two-role", {"qr_threads": 1}, False), ("fused", {}, True)]),
+    "qr128": ("qr", 128, [("default", {}, False), ("two-role", {"qr_threads": 1}, False), ("fused", {}, True), ("two-role+fused", {"qr_threads": 1}, True)]),
     "chol16": ("chol", 16, [("default", {}, False)]),
 }
 
