@@ -912,8 +912,30 @@ cudaError_t cholesky128_exact(const float* A, float* L, long batch, int fused, c
     return cudaGetLastError();
 }
 
+// entry points for the exact blocked path (blocked_exact.cu): the bit-identical 128 x 128 kernel on the diagonal
+// block at (o, o) of every matrix, and the zero fill of the blocks above the block diagonal
+cudaError_t chol_diag_exact(const float* S, float* L, int n, int o, long batch, cudaStream_t st) {
+    auto kern = blk_diag_kernel<DIAG_EXACT, false>;
+    cudaError_t e = ensure_dynamic_smem(kern, kDiagSmem);
+    if (e != cudaSuccess) return e;
+    ProfScope ps(HLSD_PROF_DIAG, st);
+    kern<<<(unsigned)batch, 512, kDiagSmem, st>>>(S, L, nullptr, n, o);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t chol_zero_upper_blocks(float* L, int n, long batch, cudaStream_t st) {
+    const int panels = n / NB;
+    ProfScope ps(HLSD_PROF_OTHER, st);
+    blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, (unsigned)batch), 256, 0, st>>>(L, n);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t cholesky_blocked_exact(const float* A, float* L, int n, long batch, cudaStream_t st);  // blocked_exact.cu
+
 cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int use_tensor, cudaStream_t st) {
-    if (n % NB != 0 || n < 2 * NB || !use_tensor) return cudaErrorNotSupported;
+    if (!use_tensor) return cholesky_blocked_exact(A, L, n, batch, st);
+    if (n % NB != 0 || n < 2 * NB) return cudaErrorNotSupported;
     if ((((uintptr_t)A | (uintptr_t)L) & 15) != 0) return cudaErrorNotSupported;
     if (batch == 0) return cudaSuccess;
     if (batch > 65535) return cudaErrorNotSupported;

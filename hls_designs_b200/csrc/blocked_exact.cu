@@ -1,0 +1,230 @@
+// HLSD_PATH_BLOCKED: blocked right-looking Cholesky for large N (N a multiple of 128, N >= 256) in the reference's
+// EXACT arithmetic - bit-identical to the csim of the right-looking designs (cholesky_v1.3 / v3.2 / v4.0,
+// Cholesky/cholesky_v1.3/model4x4/chol.cpp:25-63), at 10-25x the speed of the one-CTA-per-matrix global-memory kernel.
+//
+// Why blocking keeps the bits: in the reference element (i, j), i >= j, receives  a_ij = a_ij - l_ik * l_jk  (one
+// rounded multiply, one rounded subtract) for k = 0 .. j-1 in ascending order, then a square root (i = j) or a
+// division by l_jj.  Any schedule that applies those updates to each element in ascending k reproduces the result;
+// a right-looking sweep over 128-column panels does (panel q's updates reach every trailing element before panel
+// q+1's), and inside a panel so do the three kernels below:
+//   1. blk_diag_kernel<DIAG_EXACT>  (blocked.cu)  L11 = chol(X[q][q]), the bit-identical 128 x 128 kernel
+//   2. xchol_panel_kernel   rows below the diagonal block: for k in the panel, ascending:
+//                           x_ik = (x_ik - sum_{k' < k in panel, ascending} x_ik' l_kk') / l_kk
+//                           64 rows per CTA; by 32-column sub-blocks: 2 x 4 register tiles for the part that comes
+//                           from earlier sub-blocks, then one thread per row through the 32 x 32 triangle
+//   3. xchol_update_kernel  trailing matrix: c_ij = c_ij - l_ik * l_jk for the panel's 128 k in ascending order,
+//                           64 x 64 tiles, 4 x 4 per thread, operands transposed in shared memory so that a step is
+//                           two 16-byte loads and sixteen multiply-subtract pairs
+// The operand A is never copied: panel 0 reads its inputs from A and writes to L; later panels work in place in L.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace hlsd {
+
+constexpr int XB = 128;  // panel width
+constexpr int XR = 64;   // rows per CTA of the panel kernel / tile edge of the update kernel
+
+struct XPanelSmem {
+    static constexpr int LDX = XB + 4;                 // row stride (floats) of both tiles: 16-byte aligned rows
+    static constexpr int kX = XR * LDX, kL = XB * LDX;  // X tile (XR rows of the panel), L11
+    static constexpr int kBytes = (kX + kL) * 4;
+};
+
+// grid: (row tiles below the diagonal block, batch); 256 threads
+__global__ void __launch_bounds__(256, 2)
+xchol_panel_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int o) {
+    constexpr int LDX = XPanelSmem::LDX;
+    extern __shared__ __align__(16) float xp_smem[];
+    float* Xs = xp_smem;                    // [XR][LDX]
+    float* Ls = xp_smem + XPanelSmem::kX;   // [XB][LDX]: L11 (lower triangle incl. diagonal)
+    const int tid = threadIdx.x;
+    const long mat = (long)blockIdx.y * n * n;
+    const int row0 = o + XB + blockIdx.x * XR;  // first row of this CTA
+    const float* xsrc = S + mat + (long)row0 * n + o;  // S = A for panel 0, L afterwards
+    const float* lsrc = L + mat + (long)o * n + o;     // L11, written by the diagonal-block kernel
+    for (int e = tid; e < XR * (XB / 4); e += 256) {
+        const int r = e >> 5, c4 = e & 31;
+        *reinterpret_cast<float4*>(Xs + r * LDX + 4 * c4) = *(reinterpret_cast<const float4*>(xsrc + (long)r * n) + c4);
+    }
+    for (int e = tid; e < XB * (XB / 4); e += 256) {
+        const int r = e >> 5, c4 = e & 31;
+        *reinterpret_cast<float4*>(Ls + r * LDX + 4 * c4) = *(reinterpret_cast<const float4*>(lsrc + (long)r * n) + c4);
+    }
+    __syncthreads();
+    for (int s = 0; s < 4; s++) {
+        const int c0 = 32 * s;
+        if (s > 0) {
+            // (a) columns c0 .. c0+31 receive the updates of the panel's earlier sub-blocks, k = 0 .. c0-1 ascending:
+            //     thread -> rows (r, r+1) x columns (c .. c+3); per four k: 6 float4 loads, 32 multiply-subtract pairs
+            const int r = 2 * (tid >> 3), c = c0 + 4 * (tid & 7);
+            float x[2][4];
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+                const float4 v = *reinterpret_cast<const float4*>(Xs + (r + a) * LDX + c);
+                x[a][0] = v.x, x[a][1] = v.y, x[a][2] = v.z, x[a][3] = v.w;
+            }
+            for (int k4 = 0; k4 < c0 / 4; k4++) {
+                float xa[2][4], lb[4][4];
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+                    const float4 v = *reinterpret_cast<const float4*>(Xs + (r + a) * LDX + 4 * k4);
+                    xa[a][0] = v.x, xa[a][1] = v.y, xa[a][2] = v.z, xa[a][3] = v.w;
+                }
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const float4 v = *reinterpret_cast<const float4*>(Ls + (c + b) * LDX + 4 * k4);
+                    lb[b][0] = v.x, lb[b][1] = v.y, lb[b][2] = v.z, lb[b][3] = v.w;
+                }
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++)  // ascending k
+#pragma unroll
+                    for (int a = 0; a < 2; a++)
+#pragma unroll
+                        for (int b = 0; b < 4; b++) x[a][b] = xmsub(x[a][b], xa[a][kk], lb[b][kk]);
+            }
+            // (columns < c0 are final and every element of columns >= c0 belongs to one thread: no hazard)
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+                *reinterpret_cast<float4*>(Xs + (r + a) * LDX + c) = make_float4(x[a][0], x[a][1], x[a][2], x[a][3]);
+            __syncthreads();
+        }
+        // (b) the 32 x 32 triangle of the sub-block, one thread per row:
+        //     x_c = (x_c - sum_{m < c, ascending} x_m * l_{c0+c, c0+m}) / l_{c0+c, c0+c}
+        if (tid < XR) {
+            float* xrow = Xs + tid * LDX + c0;
+            float x[32];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const float4 v = reinterpret_cast<const float4*>(xrow)[q];
+                x[4 * q] = v.x, x[4 * q + 1] = v.y, x[4 * q + 2] = v.z, x[4 * q + 3] = v.w;
+            }
+            static_for<0, 32>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                const float4* lrow = reinterpret_cast<const float4*>(Ls + (c0 + c) * LDX + c0);
+                float acc = x[c];
+                static_for<0, c / 4 + 1>([&](auto qc) {
+                    constexpr int q = decltype(qc)::value;
+                    const float4 lv = lrow[q];
+                    if constexpr (4 * q < c) acc = xmsub(acc, x[4 * q], lv.x);
+                    if constexpr (4 * q + 1 < c) acc = xmsub(acc, x[4 * q + 1], lv.y);
+                    if constexpr (4 * q + 2 < c) acc = xmsub(acc, x[4 * q + 2], lv.z);
+                    if constexpr (4 * q + 3 < c) acc = xmsub(acc, x[4 * q + 3], lv.w);
+                    if constexpr (4 * q == (c & ~3)) {  // the piece that holds the diagonal element
+                        const float d = (c & 3) == 0 ? lv.x : ((c & 3) == 1 ? lv.y : ((c & 3) == 2 ? lv.z : lv.w));
+                        x[c] = xdiv(acc, d);
+                    }
+                });
+            });
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                reinterpret_cast<float4*>(xrow)[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+        }
+        __syncthreads();
+    }
+    float* dst = L + mat + (long)row0 * n + o;
+    for (int e = tid; e < XR * (XB / 4); e += 256) {
+        const int r = e >> 5, c4 = e & 31;
+        *(reinterpret_cast<float4*>(dst + (long)r * n) + c4) = *reinterpret_cast<const float4*>(Xs + r * LDX + 4 * c4);
+    }
+}
+
+struct XUpdSmem {
+    static constexpr int LDK = XR + 4;                 // row stride of the transposed operand tiles [k][row]
+    static constexpr int kOp = XB * LDK;
+    static constexpr int kBytes = 2 * kOp * 4;
+};
+
+// grid: (lower-triangular 64 x 64 tiles of the trailing matrix, batch); 256 threads; thread -> 4 x 4 outputs
+__global__ void __launch_bounds__(256, 3)
+xchol_update_kernel(const float* __restrict__ Csrc, float* __restrict__ L, int n, int o) {
+    constexpr int LDK = XUpdSmem::LDK;
+    extern __shared__ __align__(16) float xu_smem[];
+    float* As = xu_smem;                  // [XB k][LDK]: As[k][i] = L[ri0 + i][o + k]
+    float* Bs = xu_smem + XUpdSmem::kOp;  // [XB k][LDK]: Bs[k][j] = L[rj0 + j][o + k]
+    const int tid = threadIdx.x;
+    // unrank blockIdx.x into (ti, tj), ti >= tj
+    int rr = blockIdx.x;
+    int ti = (int)((sqrtf(8.0f * rr + 1.0f) - 1.0f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= rr) ti++;
+    while (ti * (ti + 1) / 2 > rr) ti--;
+    const int tj = rr - ti * (ti + 1) / 2;
+    const long mat = (long)blockIdx.y * n * n;
+    const int base = o + XB;  // first row / column of the trailing matrix
+    const int ri0 = base + ti * XR, rj0 = base + tj * XR;
+    const float* Lm = L + mat;
+    // transposing loads: thread reads 16 bytes along k of one row and scatters them to four k rows of the tile;
+    // consecutive threads take consecutive rows, so the scattered stores are conflict-free
+    for (int e = tid; e < XR * (XB / 4); e += 256) {
+        const int i = e & (XR - 1), k4 = e >> 6;
+        const float4 va = *(reinterpret_cast<const float4*>(Lm + (long)(ri0 + i) * n + o) + k4);
+        As[(4 * k4) * LDK + i] = va.x, As[(4 * k4 + 1) * LDK + i] = va.y;
+        As[(4 * k4 + 2) * LDK + i] = va.z, As[(4 * k4 + 3) * LDK + i] = va.w;
+        if (ti != tj) {
+            const float4 vb = *(reinterpret_cast<const float4*>(Lm + (long)(rj0 + i) * n + o) + k4);
+            Bs[(4 * k4) * LDK + i] = vb.x, Bs[(4 * k4 + 1) * LDK + i] = vb.y;
+            Bs[(4 * k4 + 2) * LDK + i] = vb.z, Bs[(4 * k4 + 3) * LDK + i] = vb.w;
+        }
+    }
+    const float* Bt = (ti != tj) ? Bs : As;
+    const int i0 = 4 * (tid >> 4), j0 = 4 * (tid & 15);
+    float c[4][4];
+    const float* csrc = Csrc + mat + (long)(ri0 + i0) * n + rj0 + j0;  // Csrc = A for panel 0, L afterwards
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        const float4 v = *reinterpret_cast<const float4*>(csrc + (long)a * n);
+        c[a][0] = v.x, c[a][1] = v.y, c[a][2] = v.z, c[a][3] = v.w;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < XB; k++) {  // ascending k: the reference's order for every element
+        const float4 av = *reinterpret_cast<const float4*>(As + k * LDK + i0);
+        const float4 bv = *reinterpret_cast<const float4*>(Bt + k * LDK + j0);
+        const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) c[a][b] = xmsub(c[a][b], a4[a], b4[b]);
+    }
+    float* cdst = L + mat + (long)(ri0 + i0) * n + rj0 + j0;
+#pragma unroll
+    for (int a = 0; a < 4; a++) *reinterpret_cast<float4*>(cdst + (long)a * n) = make_float4(c[a][0], c[a][1], c[a][2], c[a][3]);
+}
+
+// blocked.cu
+cudaError_t chol_diag_exact(const float* S, float* L, int n, int o, long batch, cudaStream_t st);
+cudaError_t chol_zero_upper_blocks(float* L, int n, long batch, cudaStream_t st);
+
+cudaError_t cholesky_blocked_exact(const float* A, float* L, int n, long batch, cudaStream_t st) {
+    if (n % XB != 0 || n < 2 * XB) return cudaErrorNotSupported;
+    if ((((uintptr_t)A | (uintptr_t)L) & 15) != 0) return cudaErrorNotSupported;
+    if (batch == 0) return cudaSuccess;
+    if (batch > 65535) return cudaErrorNotSupported;
+    cudaError_t e;
+    if ((e = ensure_dynamic_smem(xchol_panel_kernel, XPanelSmem::kBytes)) != cudaSuccess) return e;
+    if ((e = ensure_dynamic_smem(xchol_update_kernel, XUpdSmem::kBytes)) != cudaSuccess) return e;
+    const int panels = n / XB;
+    const unsigned nb = (unsigned)batch;
+    if ((e = chol_zero_upper_blocks(L, n, batch, st)) != cudaSuccess) return e;
+    for (int q = 0; q < panels; q++) {
+        const int o = q * XB;
+        const float* src = (q == 0) ? A : L;  // where the not yet factored part currently lives
+        if ((e = chol_diag_exact(src, L, n, o, batch, st)) != cudaSuccess) return e;
+        const int below = n - o - XB;
+        if (below > 0) {
+            {
+                ProfScope ps(HLSD_PROF_PANEL, st);
+                xchol_panel_kernel<<<dim3(below / XR, nb), 256, XPanelSmem::kBytes, st>>>(src, L, n, o);
+                count_launch();
+            }
+            {
+                ProfScope ps(HLSD_PROF_UPDATE, st);
+                const int m = below / XR;
+                xchol_update_kernel<<<dim3(m * (m + 1) / 2, nb), 256, XUpdSmem::kBytes, st>>>(src, L, n, o);
+                count_launch();
+            }
+        }
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace hlsd

@@ -68,8 +68,9 @@ typedef enum {
                                N in {4, 8, 16, 32, 64}, Cholesky also 128; exact                      */
 #define HLSD_PATH_GROUP 2   /* warp/CTA per matrix, shared-memory resident; exact                     */
 #define HLSD_PATH_GLOBAL 3  /* one CTA per matrix in global memory: any N, exact, slow                */
-#define HLSD_PATH_BLOCKED 4 /* reserved (blocked with an exact-order SIMT trailing update): not built,
-                               returns HLSD_ERR_UNSUPPORTED                                            */
+#define HLSD_PATH_BLOCKED 4 /* blocked right-looking Cholesky with an exact-order SIMT trailing update: bit-identical
+                               to the csim like GLOBAL, 10-25x faster; right-looking designs, n >= 256,
+                               n % 128 == 0, 16-byte aligned buffers.  LU: not built (HLSD_ERR_UNSUPPORTED)   */
 #define HLSD_PATH_TENSOR 5  /* blocked, tcgen05 tensor-core trailing update (3xTF32, fp32 accumulate):
                                Cholesky n >= 256, n % 128 == 0; LU 256 <= n <= 1024, n % 128 == 0;
                                16-byte aligned buffers.  NOT bit-identical to the csim: element-wise
@@ -80,7 +81,8 @@ typedef enum {
  * kernels for n <= ~230, and for the right-looking Cholesky designs / the pivoted LU designs at the
  * sizes and alignment listed under HLSD_PATH_TENSOR the tensor path (so AUTO at n = 256, 512, 1024 is
  * tolerance-exact, and an unaligned pointer or n = 255 stays bit-exact).  Callers that need the csim's
- * bits at every size set HLSD_FLAG_EXACT; the drop-in top() headers (hls_designs_b200/host/) do. */
+ * bits at every size set HLSD_FLAG_EXACT (AUTO then picks HLSD_PATH_BLOCKED where it applies, the register /
+ * shared-memory / global kernels elsewhere); the drop-in top() headers (hls_designs_b200/host/) do. */
 #define HLSD_FLAG_EXACT 0x100 /* never leave the reference design's arithmetic: AUTO does not select the
                                  tensor path.  With HLSD_PATH_TENSOR: HLSD_ERR_INVALID                 */
 #define HLSD_FLAG_FUSED 0x200 /* opt-in speed mode of the register-resident kernels (n in 4..128): the

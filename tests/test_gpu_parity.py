@@ -79,7 +79,9 @@ def test_reference_large_operands_exact(golden_large, n):
     for d, key in (("cholesky_v1.3", "cholesky_v1.3"), ("cholesky_v4.0", "cholesky_v1.3"), ("cholesky_v3.2", "cholesky_v1.3"),
                    ("cholesky_v2.2", "cholesky_v2.2")):
         want = golden_large[f"chol_L_{key}_{n}"]
-        for kw in (dict(path="global"), dict(exact=True)):
+        # global = one CTA per matrix in global memory; exact=True = HLSD_FLAG_EXACT, which selects the blocked exact
+        # path (HLSD_PATH_BLOCKED) for the right-looking designs and the global kernel for cholesky_v2.2
+        for kw in (dict(path="global"), dict(exact=True)) + ((dict(path="blocked"),) if key == "cholesky_v1.3" else ()):
             L = hd.cholesky(A, design=d, **kw)
             assert bits_equal(L, want), f"{d} n={n} {kw}: {first_mismatch(L, want)}"
     B = read_operand(os.path.join(ROOT, "tests", "golden", "operands", f"LU_op{n}.bin"))[None]
@@ -149,6 +151,31 @@ def test_library_vs_handwritten_model4x4():
     for path in ("auto", "group", "global"):
         Q, R = hd.qr(C, design="qr_v2.1", path=path)
         assert bits_equal(Q, Qt) and bits_equal(R, Rt), path
+
+
+@pytest.mark.parametrize("n,batch", ((256, 9), (384, 5), (512, 4), (640, 2), (1024, 3)))
+def test_blocked_exact_cholesky_vs_oracle(n, batch):
+    """HLSD_PATH_BLOCKED: 128-column panels, SIMT trailing update in the reference's per-element order: bit-identical
+    to the oracle (and to the one-CTA-per-matrix kernel) on SPD batches, on a matrix that is not positive definite
+    (NaN pattern included) and through the device-pointer entry point."""
+    import torch
+    A = gen_spd(n, batch=batch, seed=7000 + n)
+    A[batch - 1, n // 2, n // 2] = -1.0  # not positive definite from here on: NaNs must appear where the csim has them
+    want = restate.cholesky(A, threads=8)
+    got = hd.cholesky(A, path="blocked")
+    assert bits_equal(got[:batch - 1], want[:batch - 1]), f"n={n}: {first_mismatch(got[:batch - 1], want[:batch - 1])}"
+    # the indefinite matrix: NaNs in the same places (their payload bits are the hardware's), same bits elsewhere
+    gn, wn = np.isnan(got[batch - 1]), np.isnan(want[batch - 1])
+    assert wn.any() and np.array_equal(gn, wn)
+    assert bits_equal(np.where(wn, 0.0, got[batch - 1]).astype(np.float32), np.where(wn, 0.0, want[batch - 1]).astype(np.float32))
+    assert bits_equal(hd.cholesky(A, exact=True)[:batch - 1], want[:batch - 1])
+    assert bits_equal(hd.cholesky(torch.from_numpy(A).cuda(), path="blocked").cpu().numpy()[:batch - 1], want[:batch - 1])
+    assert bits_equal(hd.cholesky(A, path="global")[:batch - 1], got[:batch - 1])
+    assert chol_residual(A[:batch - 1], got[:batch - 1]).max() < 2e-6
+    with pytest.raises(hd.HlsdError):
+        hd.cholesky(A, design="cholesky_v2.2", path="blocked")
+    with pytest.raises(hd.HlsdError):
+        hd.cholesky(gen_spd(200), path="blocked")
 
 
 # ---------------------------------------------------------------- HLSD_FLAG_FUSED (opt-in contraction)
