@@ -1097,6 +1097,10 @@ __device__ __forceinline__ PivCand piv_better(PivCand a, PivCand b) {
 
 // Panel factorisation: one CTA per matrix, thread t = row o + t of the working matrix (blockDim = rows of
 // the panel, at least 256 because threads 0..191 also serve as column workers between sub-panels).
+// EXACT: the reference's arithmetic (IEEE division, separately rounded multiply and subtract); the per-element
+// operation order is the reference's in both modes (every update arrives in ascending k), so with EXACT the panel -
+// and with the exact U12 / trailing-update kernels of blocked_exact.cu the whole factorisation - is bit-identical.
+template <bool EXACT>
 __global__ void __launch_bounds__(1024, 1)
 lu_panel_kernel(float* __restrict__ Wk, float* __restrict__ L, int* __restrict__ P, int n, int o) {
     // double buffered by column parity: two barriers per column are enough (after the search partials, after the
@@ -1183,10 +1187,10 @@ lu_panel_kernel(float* __restrict__ Wk, float* __restrict__ L, int* __restrict__
                 }
             }
             if (live && row > k) {
-                const float l = a[kk] / urow[kk];
+                const float l = EXACT ? xdiv(a[kk], urow[kk]) : a[kk] / urow[kk];
                 a[kk] = l;
 #pragma unroll
-                for (int j = kk + 1; j < 32; j++) a[j] = fmaf(-l, urow[j], a[j]);
+                for (int j = kk + 1; j < 32; j++) a[j] = EXACT ? xmsub(a[j], l, urow[j]) : fmaf(-l, urow[j], a[j]);
             }
         });
         // write the sub-panel: multipliers to L (unit diagonal, zeros above), U11 entries to the working matrix
@@ -1243,7 +1247,7 @@ lu_panel_kernel(float* __restrict__ Wk, float* __restrict__ L, int* __restrict__
                 for (int i = 0; i < 32; i++) {
                     float s = col[(long)(cs + i) * n];
 #pragma unroll
-                    for (int kk = 0; kk < i; kk++) s = fmaf(-l11[i][kk], x[kk], s);
+                    for (int kk = 0; kk < i; kk++) s = EXACT ? xmsub(s, l11[i][kk], x[kk]) : fmaf(-l11[i][kk], x[kk], s);
                     x[i] = s;
                     col[(long)(cs + i) * n] = s;
                     ublk[i][t] = s;
@@ -1258,8 +1262,13 @@ lu_panel_kernel(float* __restrict__ Wk, float* __restrict__ L, int* __restrict__
 #pragma unroll
                     for (int kk = 0; kk < 32; kk++) {
                         const float4 u = *reinterpret_cast<const float4*>(&ublk[kk][4 * q]);
-                        v.x = fmaf(-a[kk], u.x, v.x), v.y = fmaf(-a[kk], u.y, v.y);
-                        v.z = fmaf(-a[kk], u.z, v.z), v.w = fmaf(-a[kk], u.w, v.w);
+                        if constexpr (EXACT) {
+                            v.x = xmsub(v.x, a[kk], u.x), v.y = xmsub(v.y, a[kk], u.y);
+                            v.z = xmsub(v.z, a[kk], u.z), v.w = xmsub(v.w, a[kk], u.w);
+                        } else {
+                            v.x = fmaf(-a[kk], u.x, v.x), v.y = fmaf(-a[kk], u.y, v.y);
+                            v.z = fmaf(-a[kk], u.z, v.z), v.w = fmaf(-a[kk], u.w, v.w);
+                        }
                     }
                     dst[q] = v;
                 }
@@ -1431,7 +1440,7 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
         // thread = row of the panel: later panels are shorter and run with fewer (cheaper to synchronise) threads
         {
             ProfScope ps(HLSD_PROF_PANEL, st);
-            lu_panel_kernel<<<nb, std::max(256, n - o), 0, st>>>(U, L, P, n, o);
+            lu_panel_kernel<false><<<nb, std::max(256, n - o), 0, st>>>(U, L, P, n, o);
             count_launch();
         }
         if (mt == 0) {  // last panel: nothing to update, only its L columns go back to the reference's convention
@@ -1492,6 +1501,58 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
     e = cudaGetLastError();
     ws_free(ws, st);
     return e;
+}
+
+// Blocked LU in the reference's exact arithmetic (HLSD_FLAG_EXACT / HLSD_PATH_BLOCKED, 256 <= n <= 1024): the structure
+// of lu_blocked with every arithmetic step exact and in the reference's per-element order - the pivoted panel kernel
+// in exact mode, the same exchange / un-exchange kernels (pure data movement), U12 by forward substitution and the
+// trailing update on SIMT tiles (blocked_exact.cu).  Bit-identical to the csim: L, U and P.
+cudaError_t xlu_u12_and_update(float* Wk, const float* L, int n, int o, long batch, cudaStream_t st);  // blocked_exact.cu
+
+cudaError_t lu_blocked_exact(const float* A, float* L, float* U, int* P, int n, long batch, cudaStream_t st) {
+    if (n % NB != 0 || n < 2 * NB || n > 1024) return cudaErrorNotSupported;
+    if ((((uintptr_t)A | (uintptr_t)L | (uintptr_t)U) & 15) != 0) return cudaErrorNotSupported;
+    if (batch == 0) return cudaSuccess;
+    if (batch > 65535) return cudaErrorNotSupported;
+    cudaError_t e;
+    const size_t unswap_smem = (size_t)2 * NB * (NB + 1) * sizeof(float) + (size_t)n * sizeof(int);
+    if ((e = ensure_dynamic_smem(lu_unswap_panel_kernel, unswap_smem)) != cudaSuccess) return e;
+    const unsigned nb = (unsigned)batch;
+    const long nn = (long)n * n;
+    {
+        ProfScope ps(HLSD_PROF_OTHER, st);
+        e = cudaMemcpyAsync(U, A, sizeof(float) * (size_t)batch * nn, cudaMemcpyDeviceToDevice, st);
+    }
+    if (e != cudaSuccess) return e;
+    const int panels = n / NB;
+    {
+        ProfScope ps(HLSD_PROF_OTHER, st);
+        blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, nb), 256, 0, st>>>(L, n);
+        count_launch();
+    }
+    for (int p = 0; p < panels; p++) {
+        const int o = p * NB;
+        const int ncols = (panels - p - 1) * NB;
+        {
+            ProfScope ps(HLSD_PROF_PANEL, st);
+            lu_panel_kernel<true><<<nb, std::max(256, n - o), 0, st>>>(U, L, P, n, o);
+            count_launch();
+        }
+        if (ncols > 0) {
+            {
+                ProfScope ps(HLSD_PROF_PERMUTE, st);
+                lu_swap_kernel<<<dim3((ncols + 127) / 128, nb), 128, n * sizeof(int), st>>>(U, P, n, o);
+                count_launch();
+            }
+            if ((e = xlu_u12_and_update(U, L, n, o, batch, st)) != cudaSuccess) return e;
+        }
+        {
+            ProfScope ps(HLSD_PROF_PERMUTE, st);
+            lu_unswap_panel_kernel<<<nb, kUnswapThreads, unswap_smem, st>>>(L, P, n, o);  // L21 has served as operand
+            count_launch();
+        }
+    }
+    return cudaGetLastError();
 }
 
 }  // namespace hlsd

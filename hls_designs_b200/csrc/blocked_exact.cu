@@ -16,6 +16,14 @@
 //                           64 x 64 tiles, 4 x 4 per thread, operands transposed in shared memory so that a step is
 //                           two 16-byte loads and sixteen multiply-subtract pairs
 // The operand A is never copied: panel 0 reads its inputs from A and writes to L; later panels work in place in L.
+//
+// Blocked exact LU (lu_blocked_exact in blocked.cu, 256 <= N <= 1024): the pivoted panel kernel of the tensor path
+// in exact arithmetic (lu_panel_kernel<true>), its exchange / un-exchange kernels, and two kernels from this file:
+//   xchol_panel_kernel<1>   U12 = L11^-1 A12 by forward substitution in the reference's order
+//                           (u_kj = a_kj - sum_{k' < k, ascending} l_kk' u_k'j; the same recurrence as the Cholesky
+//                           panel solve with rows and columns swapped and a unit diagonal: the tile is transposed
+//                           on its way into shared memory)
+//   xchol_update_kernel<1>  A22[i][j] = A22[i][j] - l_ik * u_kj, k ascending, all 64 x 64 tiles
 #include "common.cuh"
 #include "kernels.h"
 
@@ -30,21 +38,37 @@ struct XPanelSmem {
     static constexpr int kBytes = (kX + kL) * 4;
 };
 
-// grid: (row tiles below the diagonal block, batch); 256 threads
+// MODE 0 (Cholesky): grid (row tiles below the diagonal block, batch); X tile = XR rows x 128 panel columns of S
+//                    (= A for panel 0, L afterwards), result to L.
+// MODE 1 (LU, U12):  grid (64-column tiles right of the panel, batch); the tile is 128 panel ROWS x XR columns of
+//                    the working matrix S (= the U buffer), kept TRANSPOSED in shared memory (Xs[j][k]); unit
+//                    diagonal: no division; result back into S's buffer through `X`.
+// 256 threads
+template <int MODE>
 __global__ void __launch_bounds__(256, 2)
-xchol_panel_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int o) {
+xchol_panel_kernel(const float* __restrict__ S, float* __restrict__ X, const float* __restrict__ L, int n, int o) {
     constexpr int LDX = XPanelSmem::LDX;
     extern __shared__ __align__(16) float xp_smem[];
     float* Xs = xp_smem;                    // [XR][LDX]
     float* Ls = xp_smem + XPanelSmem::kX;   // [XB][LDX]: L11 (lower triangle incl. diagonal)
     const int tid = threadIdx.x;
     const long mat = (long)blockIdx.y * n * n;
-    const int row0 = o + XB + blockIdx.x * XR;  // first row of this CTA
-    const float* xsrc = S + mat + (long)row0 * n + o;  // S = A for panel 0, L afterwards
-    const float* lsrc = L + mat + (long)o * n + o;     // L11, written by the diagonal-block kernel
-    for (int e = tid; e < XR * (XB / 4); e += 256) {
-        const int r = e >> 5, c4 = e & 31;
-        *reinterpret_cast<float4*>(Xs + r * LDX + 4 * c4) = *(reinterpret_cast<const float4*>(xsrc + (long)r * n) + c4);
+    const int row0 = o + XB + blockIdx.x * XR;  // MODE 0: first row of this CTA; MODE 1: first column
+    const float* xsrc = MODE == 0 ? S + mat + (long)row0 * n + o : S + mat + (long)o * n + row0;
+    const float* lsrc = L + mat + (long)o * n + o;     // L11, written by the diagonal-block / panel kernel
+    if constexpr (MODE == 0) {
+        for (int e = tid; e < XR * (XB / 4); e += 256) {
+            const int r = e >> 5, c4 = e & 31;
+            *reinterpret_cast<float4*>(Xs + r * LDX + 4 * c4) = *(reinterpret_cast<const float4*>(xsrc + (long)r * n) + c4);
+        }
+    } else {
+        // transposing load: consecutive threads take consecutive panel rows k, so the scattered stores are conflict-free
+        for (int e = tid; e < XB * (XR / 4); e += 256) {
+            const int k = e & (XB - 1), j4 = e >> 7;
+            const float4 v = *(reinterpret_cast<const float4*>(xsrc + (long)k * n) + j4);
+            Xs[(4 * j4) * LDX + k] = v.x, Xs[(4 * j4 + 1) * LDX + k] = v.y;
+            Xs[(4 * j4 + 2) * LDX + k] = v.z, Xs[(4 * j4 + 3) * LDX + k] = v.w;
+        }
     }
     for (int e = tid; e < XB * (XB / 4); e += 256) {
         const int r = e >> 5, c4 = e & 31;
@@ -111,7 +135,7 @@ xchol_panel_kernel(const float* __restrict__ S, float* __restrict__ L, int n, in
                     if constexpr (4 * q + 3 < c) acc = xmsub(acc, x[4 * q + 3], lv.w);
                     if constexpr (4 * q == (c & ~3)) {  // the piece that holds the diagonal element
                         const float d = (c & 3) == 0 ? lv.x : ((c & 3) == 1 ? lv.y : ((c & 3) == 2 ? lv.z : lv.w));
-                        x[c] = xdiv(acc, d);
+                        x[c] = MODE == 0 ? xdiv(acc, d) : acc;  // (LU: unit diagonal)
                     }
                 });
             });
@@ -121,10 +145,19 @@ xchol_panel_kernel(const float* __restrict__ S, float* __restrict__ L, int n, in
         }
         __syncthreads();
     }
-    float* dst = L + mat + (long)row0 * n + o;
-    for (int e = tid; e < XR * (XB / 4); e += 256) {
-        const int r = e >> 5, c4 = e & 31;
-        *(reinterpret_cast<float4*>(dst + (long)r * n) + c4) = *reinterpret_cast<const float4*>(Xs + r * LDX + 4 * c4);
+    if constexpr (MODE == 0) {
+        float* dst = X + mat + (long)row0 * n + o;
+        for (int e = tid; e < XR * (XB / 4); e += 256) {
+            const int r = e >> 5, c4 = e & 31;
+            *(reinterpret_cast<float4*>(dst + (long)r * n) + c4) = *reinterpret_cast<const float4*>(Xs + r * LDX + 4 * c4);
+        }
+    } else {
+        float* dst = X + mat + (long)o * n + row0;
+        for (int e = tid; e < XB * (XR / 4); e += 256) {
+            const int k = e & (XB - 1), j4 = e >> 7;
+            *(reinterpret_cast<float4*>(dst + (long)k * n) + j4) =
+                make_float4(Xs[(4 * j4) * LDX + k], Xs[(4 * j4 + 1) * LDX + k], Xs[(4 * j4 + 2) * LDX + k], Xs[(4 * j4 + 3) * LDX + k]);
+        }
     }
 }
 
@@ -134,20 +167,32 @@ struct XUpdSmem {
     static constexpr int kBytes = 2 * kOp * 4;
 };
 
-// grid: (lower-triangular 64 x 64 tiles of the trailing matrix, batch); 256 threads; thread -> 4 x 4 outputs
+// LU == 0 (Cholesky): grid (lower-triangular 64 x 64 tiles of the trailing matrix, batch); C: Csrc -> Cdst (= L),
+//                      both operands are rows of L.
+// LU == 1:             grid (all tiles, batch); C in place in the working matrix (Csrc = Cdst = the U buffer); A operand
+//                      = rows of L (multipliers, final row order), B operand = rows o..o+127 of the working matrix (U12),
+//                      which are already [k][j].
+// 256 threads; thread -> 4 x 4 outputs
+template <int LU>
 __global__ void __launch_bounds__(256, 3)
-xchol_update_kernel(const float* __restrict__ Csrc, float* __restrict__ L, int n, int o) {
+xchol_update_kernel(const float* __restrict__ Csrc, float* __restrict__ Cdst, const float* __restrict__ L, int n, int o) {
     constexpr int LDK = XUpdSmem::LDK;
     extern __shared__ __align__(16) float xu_smem[];
     float* As = xu_smem;                  // [XB k][LDK]: As[k][i] = L[ri0 + i][o + k]
-    float* Bs = xu_smem + XUpdSmem::kOp;  // [XB k][LDK]: Bs[k][j] = L[rj0 + j][o + k]
+    float* Bs = xu_smem + XUpdSmem::kOp;  // [XB k][LDK]: Bs[k][j] = L[rj0 + j][o + k]  (LU: U[o + k][rj0 + j])
     const int tid = threadIdx.x;
-    // unrank blockIdx.x into (ti, tj), ti >= tj
-    int rr = blockIdx.x;
-    int ti = (int)((sqrtf(8.0f * rr + 1.0f) - 1.0f) * 0.5f);
-    while ((ti + 1) * (ti + 2) / 2 <= rr) ti++;
-    while (ti * (ti + 1) / 2 > rr) ti--;
-    const int tj = rr - ti * (ti + 1) / 2;
+    int ti, tj;
+    if constexpr (LU) {
+        const int m = (n - o - XB) / XR;
+        ti = blockIdx.x / m, tj = blockIdx.x % m;
+    } else {
+        // unrank blockIdx.x into (ti, tj), ti >= tj
+        int rr = blockIdx.x;
+        ti = (int)((sqrtf(8.0f * rr + 1.0f) - 1.0f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= rr) ti++;
+        while (ti * (ti + 1) / 2 > rr) ti--;
+        tj = rr - ti * (ti + 1) / 2;
+    }
     const long mat = (long)blockIdx.y * n * n;
     const int base = o + XB;  // first row / column of the trailing matrix
     const int ri0 = base + ti * XR, rj0 = base + tj * XR;
@@ -159,13 +204,20 @@ xchol_update_kernel(const float* __restrict__ Csrc, float* __restrict__ L, int n
         const float4 va = *(reinterpret_cast<const float4*>(Lm + (long)(ri0 + i) * n + o) + k4);
         As[(4 * k4) * LDK + i] = va.x, As[(4 * k4 + 1) * LDK + i] = va.y;
         As[(4 * k4 + 2) * LDK + i] = va.z, As[(4 * k4 + 3) * LDK + i] = va.w;
-        if (ti != tj) {
+        if (!LU && ti != tj) {
             const float4 vb = *(reinterpret_cast<const float4*>(Lm + (long)(rj0 + i) * n + o) + k4);
             Bs[(4 * k4) * LDK + i] = vb.x, Bs[(4 * k4 + 1) * LDK + i] = vb.y;
             Bs[(4 * k4 + 2) * LDK + i] = vb.z, Bs[(4 * k4 + 3) * LDK + i] = vb.w;
         }
     }
-    const float* Bt = (ti != tj) ? Bs : As;
+    if constexpr (LU) {
+        const float* Um = Csrc + mat + (long)o * n + rj0;  // rows o..o+127 of the working matrix, columns of this tile
+        for (int e = tid; e < XB * (XR / 4); e += 256) {
+            const int k = e >> 4, j4 = e & 15;
+            *reinterpret_cast<float4*>(Bs + k * LDK + 4 * j4) = *(reinterpret_cast<const float4*>(Um + (long)k * n) + j4);
+        }
+    }
+    const float* Bt = (LU || ti != tj) ? Bs : As;
     const int i0 = 4 * (tid >> 4), j0 = 4 * (tid & 15);
     float c[4][4];
     const float* csrc = Csrc + mat + (long)(ri0 + i0) * n + rj0 + j0;  // Csrc = A for panel 0, L afterwards
@@ -185,7 +237,7 @@ xchol_update_kernel(const float* __restrict__ Csrc, float* __restrict__ L, int n
 #pragma unroll
             for (int b = 0; b < 4; b++) c[a][b] = xmsub(c[a][b], a4[a], b4[b]);
     }
-    float* cdst = L + mat + (long)(ri0 + i0) * n + rj0 + j0;
+    float* cdst = Cdst + mat + (long)(ri0 + i0) * n + rj0 + j0;
 #pragma unroll
     for (int a = 0; a < 4; a++) *reinterpret_cast<float4*>(cdst + (long)a * n) = make_float4(c[a][0], c[a][1], c[a][2], c[a][3]);
 }
@@ -200,8 +252,8 @@ cudaError_t cholesky_blocked_exact(const float* A, float* L, int n, long batch, 
     if (batch == 0) return cudaSuccess;
     if (batch > 65535) return cudaErrorNotSupported;
     cudaError_t e;
-    if ((e = ensure_dynamic_smem(xchol_panel_kernel, XPanelSmem::kBytes)) != cudaSuccess) return e;
-    if ((e = ensure_dynamic_smem(xchol_update_kernel, XUpdSmem::kBytes)) != cudaSuccess) return e;
+    if ((e = ensure_dynamic_smem(xchol_panel_kernel<0>, XPanelSmem::kBytes)) != cudaSuccess) return e;
+    if ((e = ensure_dynamic_smem(xchol_update_kernel<0>, XUpdSmem::kBytes)) != cudaSuccess) return e;
     const int panels = n / XB;
     const unsigned nb = (unsigned)batch;
     if ((e = chol_zero_upper_blocks(L, n, batch, st)) != cudaSuccess) return e;
@@ -213,16 +265,37 @@ cudaError_t cholesky_blocked_exact(const float* A, float* L, int n, long batch, 
         if (below > 0) {
             {
                 ProfScope ps(HLSD_PROF_PANEL, st);
-                xchol_panel_kernel<<<dim3(below / XR, nb), 256, XPanelSmem::kBytes, st>>>(src, L, n, o);
+                xchol_panel_kernel<0><<<dim3(below / XR, nb), 256, XPanelSmem::kBytes, st>>>(src, L, L, n, o);
                 count_launch();
             }
             {
                 ProfScope ps(HLSD_PROF_UPDATE, st);
                 const int m = below / XR;
-                xchol_update_kernel<<<dim3(m * (m + 1) / 2, nb), 256, XUpdSmem::kBytes, st>>>(src, L, n, o);
+                xchol_update_kernel<0><<<dim3(m * (m + 1) / 2, nb), 256, XUpdSmem::kBytes, st>>>(src, L, L, n, o);
                 count_launch();
             }
         }
+    }
+    return cudaGetLastError();
+}
+
+// the two exact kernels of the blocked LU (called from lu_blocked_exact, blocked.cu): U12 and the trailing update of
+// the panel at offset o; Wk = working matrix (the U buffer), L = multipliers in final row order
+cudaError_t xlu_u12_and_update(float* Wk, const float* L, int n, int o, long batch, cudaStream_t st) {
+    cudaError_t e;
+    if ((e = ensure_dynamic_smem(xchol_panel_kernel<1>, XPanelSmem::kBytes)) != cudaSuccess) return e;
+    if ((e = ensure_dynamic_smem(xchol_update_kernel<1>, XUpdSmem::kBytes)) != cudaSuccess) return e;
+    const int m = (n - o - XB) / XR;
+    if (m <= 0) return cudaSuccess;
+    {
+        ProfScope ps(HLSD_PROF_TRSM, st);
+        xchol_panel_kernel<1><<<dim3(m, (unsigned)batch), 256, XPanelSmem::kBytes, st>>>(Wk, Wk, L, n, o);
+        count_launch();
+    }
+    {
+        ProfScope ps(HLSD_PROF_UPDATE, st);
+        xchol_update_kernel<1><<<dim3(m * m, (unsigned)batch), 256, XUpdSmem::kBytes, st>>>(Wk, Wk, L, n, o);
+        count_launch();
     }
     return cudaGetLastError();
 }

@@ -68,9 +68,10 @@ typedef enum {
                                N in {4, 8, 16, 32, 64}, Cholesky also 128; exact                      */
 #define HLSD_PATH_GROUP 2   /* warp/CTA per matrix, shared-memory resident; exact                     */
 #define HLSD_PATH_GLOBAL 3  /* one CTA per matrix in global memory: any N, exact, slow                */
-#define HLSD_PATH_BLOCKED 4 /* blocked right-looking Cholesky with an exact-order SIMT trailing update: bit-identical
-                               to the csim like GLOBAL, 10-25x faster; right-looking designs, n >= 256,
-                               n % 128 == 0, 16-byte aligned buffers.  LU: not built (HLSD_ERR_UNSUPPORTED)   */
+#define HLSD_PATH_BLOCKED 4 /* blocked right-looking factorisation with an exact-order SIMT trailing update:
+                               bit-identical to the csim like GLOBAL, 10-50x faster.  Cholesky: right-looking
+                               designs, n >= 256, n % 128 == 0; LU: pivoted designs, 256 <= n <= 1024,
+                               n % 128 == 0; 16-byte aligned buffers                                          */
 #define HLSD_PATH_TENSOR 5  /* blocked, tcgen05 tensor-core trailing update (3xTF32, fp32 accumulate):
                                Cholesky n >= 256, n % 128 == 0; LU 256 <= n <= 1024, n % 128 == 0;
                                16-byte aligned buffers.  NOT bit-identical to the csim: element-wise

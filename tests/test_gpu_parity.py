@@ -86,7 +86,7 @@ def test_reference_large_operands_exact(golden_large, n):
             assert bits_equal(L, want), f"{d} n={n} {kw}: {first_mismatch(L, want)}"
     B = read_operand(os.path.join(ROOT, "tests", "golden", "operands", f"LU_op{n}.bin"))[None]
     for d in LU_DESIGNS:
-        for kw in (dict(path="global"), dict(exact=True)):
+        for kw in (dict(path="global"), dict(exact=True), dict(path="blocked")):  # exact=True selects the blocked exact LU
             L, U, P = hd.lu(B, design=d, **kw)
             assert bits_equal(L, golden_large[f"lu_L_{n}"]), f"L {d} n={n} {kw}: {first_mismatch(L, golden_large[f'lu_L_{n}'])}"
             assert bits_equal(U, golden_large[f"lu_U_{n}"]), f"U {d} n={n} {kw}: {first_mismatch(U, golden_large[f'lu_U_{n}'])}"
@@ -176,6 +176,34 @@ def test_blocked_exact_cholesky_vs_oracle(n, batch):
         hd.cholesky(A, design="cholesky_v2.2", path="blocked")
     with pytest.raises(hd.HlsdError):
         hd.cholesky(gen_spd(200), path="blocked")
+
+
+@pytest.mark.parametrize("n,batch", ((256, 7), (384, 4), (512, 3), (1024, 2)))
+def test_blocked_exact_lu_vs_oracle(n, batch):
+    """HLSD_PATH_BLOCKED for LU: pivoted panel kernel in exact arithmetic, LAPACK-style exchanges inside the panel undone
+    afterwards, U12 by forward substitution and the trailing update in the reference's per-element order: L, U and P
+    bit-identical to the oracle on integer (genA) and real operands, with pivot ties and a singular matrix."""
+    import torch
+    rng = np.random.default_rng(n)
+    A = gen_full_rank(n, batch=batch, seed=8000 + n)
+    B = (rng.standard_normal((batch, n, n)) * 3).astype(np.float32)
+    B[0, :, 5] = B[0, :, 3]          # two equal columns: an exactly singular matrix (zero pivot -> inf / nan like the csim)
+    A[1, 7, :] = A[1, 3, :]          # two equal rows: pivot ties
+    for M in (A, B):
+        want = restate.lu(M, threads=8)
+        for kw in (dict(path="blocked"), dict(exact=True)):
+            got = hd.lu(M, **kw)
+            for name, g, w in zip("LUP", got, want):
+                if g.dtype == np.float32:
+                    gn, wn = np.isnan(g), np.isnan(w)
+                    assert np.array_equal(gn, wn), f"{name} n={n} {kw}: NaN pattern differs"
+                    g, w = np.where(wn, 0.0, g).astype(np.float32), np.where(wn, 0.0, w).astype(np.float32)
+                assert bits_equal(g, w), f"{name} n={n} {kw}: {first_mismatch(g, w)}"
+    got_d = hd.lu(torch.from_numpy(A).cuda(), path="blocked")
+    for g, w in zip(got_d, restate.lu(A, threads=8)):
+        assert bits_equal(g.cpu().numpy(), w)
+    with pytest.raises(hd.HlsdError):
+        hd.lu(A, design="nopivot", path="blocked")
 
 
 # ---------------------------------------------------------------- HLSD_FLAG_FUSED (opt-in contraction)

@@ -38,7 +38,7 @@ def test_auto_dispatch_uses_tensor_path_for_large_n():
         assert np.array_equal(exact.view(np.uint32), restate.cholesky(A).view(np.uint32))
     B = gen_spd(256, batch=1, seed=10) * np.float32(0.01) + np.arange(256 * 256, dtype=np.float32).reshape(256, 256) % 7
     for g, w in zip(hd.lu(B, exact=True), restate.lu(B)):
-        assert np.array_equal(g, w)
+        assert np.array_equal(g, w, equal_nan=True) if g.dtype == np.float32 else np.array_equal(g, w)
     with pytest.raises(hd.HlsdError):
         hd.cholesky(A, path="tensor", exact=True)
     # cholesky_v2.2 has no blocked form: auto falls back to the exact kernel
