@@ -16,7 +16,7 @@ import hls_designs_b200 as hd  # noqa: E402
 from bench import PROF_CLASSES  # noqa: E402
 
 CASES = [("chol", 1024, 4096), ("chol", 512, 8192), ("chol", 256, 16384), ("lu", 1024, 2048), ("lu", 512, 4096)]
-VARIANTS = [("default", {}), ("diag_kernel=1", {"diag_kernel": 1})]
+VARIANTS = [("default", {}, {}), ("diag_kernel=1", {"diag_kernel": 1}, {}), ("exact (blocked)", {}, {"exact": True})]
 
 
 def main():
@@ -37,19 +37,19 @@ def main():
             A = torch.randint(1, 101, (batch, n, n), generator=g, device=dev).float()
             fn = hd.lu
         ref = None
-        for label, opts in VARIANTS:
+        for label, opts, kw in VARIANTS:
             for k in hd.api.OPTIONS:
                 hd.set_option(k, 0)
             for k, v in opts.items():
                 hd.set_option(k, v)
             for _ in range(2):
-                out = fn(A)
+                out = fn(A, **kw)
             torch.cuda.synchronize()
             ms = []
             for _ in range(5):
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
-                out = fn(A)
+                out = fn(A, **kw)
                 e.record()
                 torch.cuda.synchronize()
                 ms.append(s.elapsed_time(e))
@@ -57,7 +57,7 @@ def main():
             prof = (ctypes.c_double * len(PROF_CLASSES))()
             cnt = (ctypes.c_int64 * len(PROF_CLASSES))()
             lib.hlsd_profile_begin()
-            fn(A)
+            fn(A, **kw)
             torch.cuda.synchronize()
             lib.hlsd_profile_end(prof, cnt, len(PROF_CLASSES))
             first = (out[0] if isinstance(out, tuple) else out)[:4].float().cpu().numpy()

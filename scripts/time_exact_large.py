@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import hls_designs_b200 as hd  # noqa: E402
 
 dev = torch.device("cuda", 0)
-for kind, n, batch in (("chol", 256, 8192), ("chol", 512, 2048), ("chol", 1024, 512), ("lu", 256, 1024), ("lu", 512, 256), ("lu", 1024, 64)):
+for kind, n, batch in (("chol", 256, 8192), ("chol", 512, 2048), ("chol", 1024, 512), ("lu", 256, 8192), ("lu", 512, 2048), ("lu", 1024, 1024)):
     g = torch.Generator(device=dev).manual_seed(1)
     if kind == "chol":
         A = torch.rand((batch, n, n), generator=g, device=dev)
