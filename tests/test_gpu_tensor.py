@@ -94,24 +94,44 @@ def test_tensor_lu_vs_oracle(n, batch):
 
 
 def test_full_size_tensor_paths_n1024_properties():
-    """configs[4] (N = 1024) on a 256-matrix slice of the batch: residuals on the device for every matrix,
-    structure of the factors, first matrices against the oracle within the documented tolerances."""
+    """configs[4] (N = 1024) on a 256-matrix slice of the batch: residuals on the device for EVERY matrix, structure of
+    the factors, and twelve matrices spread over the slice against the oracle within the documented tolerances (tensor
+    paths) and bit for bit (the exact blocked paths on the same operands)."""
     import torch
+    from conftest import lu_residual
     n, batch = 1024, 256
+    pick = np.unique(np.linspace(0, batch - 1, 12).astype(np.int64))
+    tpick = torch.from_numpy(pick).cuda()
     g = torch.Generator(device="cuda").manual_seed(5)
     A = torch.rand((batch, n, n), generator=g, device="cuda")
     S = (0.5 * (A + A.transpose(1, 2)))
     S.diagonal(dim1=1, dim2=2).add_(float(n))
+    del A
     L = hd.cholesky(S)
     res = (S - L @ L.transpose(1, 2)).flatten(1).norm(dim=1) / S.flatten(1).norm(dim=1)
     assert float(res.max()) < RESIDUAL_TOL and float(torch.triu(L, 1).abs().max()) == 0.0
-    want = restate.cholesky(S[:2].cpu().numpy(), threads=8)
-    assert np.abs(L[:2].cpu().numpy() - want).max() / np.abs(want).max() < ELEMENT_TOL
-    del L, S
+    Sh = S[tpick].cpu().numpy()
+    want = restate.cholesky(Sh, threads=8)
+    got = L[tpick].cpu().numpy()
+    assert np.abs(got - want).max() / np.abs(want).max() < ELEMENT_TOL
+    Lx = hd.cholesky(S[tpick].contiguous(), exact=True)  # blocked exact path on the same operands
+    assert np.array_equal(Lx.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    del L, S, Lx
     B = torch.randint(1, 101, (batch, n, n), generator=g, device="cuda").float()
     Ll, Uu, P = hd.lu(B)
     assert float(torch.triu(Ll, 1).abs().max()) == 0.0 and float(Ll.abs().max()) <= 1.0 + 1e-6
     assert float(torch.tril(Uu, -1).abs().max()) == 0.0
-    from conftest import lu_residual
-    Bh, Lh, Uh, Ph = (x[:3].cpu().numpy() for x in (B, Ll, Uu, P))
-    assert max(lu_residual(Bh[b], Lh[b], Uh[b], Ph[b]) for b in range(3)) < 5e-5
+    assert bool((P >= torch.arange(n, device="cuda", dtype=P.dtype)).all()) and bool((P < n).all())  # P[k] >= k: a valid exchange
+    Bh, Lh, Uh, Ph = (x[tpick].cpu().numpy() for x in (B, Ll, Uu, P))
+    wl, wu, wp = restate.lu(Bh, threads=8)
+    same = 0
+    for b in range(len(pick)):
+        assert lu_residual(Bh[b], Lh[b], Uh[b], Ph[b]) < 5e-5
+        if np.array_equal(Ph[b], wp[b]):
+            same += 1
+            assert np.abs(Lh[b] - wl[b]).max() < 1e-3 and np.abs(Uh[b] - wu[b]).max() / np.abs(wu[b]).max() < 1e-3
+    print(f"tensor LU 1024: {same} of {len(pick)} pivot sequences equal to the oracle's")
+    xl, xu, xp = hd.lu(B[tpick].contiguous(), exact=True)  # blocked exact path: bit-identical L, U, P
+    assert np.array_equal(xp.cpu().numpy(), wp)
+    assert np.array_equal(xl.cpu().numpy().view(np.uint32), wl.view(np.uint32))
+    assert np.array_equal(xu.cpu().numpy().view(np.uint32), wu.view(np.uint32))
