@@ -161,6 +161,165 @@ xchol_panel_kernel(const float* __restrict__ S, float* __restrict__ X, const flo
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Exact Cholesky of an M x M block (M = 64 or 128) held in shared memory, one CTA per matrix, blocked by 32 columns:
+//   for j = 0 .. M/32 - 1:
+//     (a) block column j receives the updates of the columns left of it, k ascending, 2 x 2 register tiles
+//     (b) ONE warp factors the 32 x 32 diagonal block: lane = row, the row in registers, pivot and column stream by
+//         shuffle, IEEE square root and division, separately rounded multiply-subtract
+//     (c) rows below: one thread per row through the 32 x 32 triangle (forward substitution, IEEE division)
+// Per element the operations and their order are the reference's (updates in ascending k, then root / division), so
+// the result is bit-identical.  Compared with the register kernels (chol_rows_kernel<64>: every step shuffles all 64
+// columns through the warp; blk_diag_kernel<EXACT>: one block-wide barrier per column) the shuffle / barrier work is
+// confined to the 32 x 32 diagonal blocks and the rest runs from shared memory with small loops that stay in the
+// instruction cache; 17 KB (M = 64) / 68 KB (M = 128) of shared memory, so many matrices share an SM and hide each
+// other's serial diagonal-block phases.  Serves N = 64 and N = 128 and, with a row stride, the diagonal blocks of
+// the blocked exact path.  FUSED: HLSD_FLAG_FUSED (a - b*c contracted).
+// ------------------------------------------------------------------------------------------------
+template <bool FUSED>
+__device__ __forceinline__ void xchol32(float* T, int ldt, int c0, int lane) {
+    float d[32];
+    {
+        const float4* row4 = reinterpret_cast<const float4*>(T + (c0 + lane) * ldt + c0);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const float4 v = row4[q];
+            d[4 * q] = v.x, d[4 * q + 1] = v.y, d[4 * q + 2] = v.z, d[4 * q + 3] = v.w;
+        }
+    }
+    static_for<0, 32>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        // lanes above row k hold scratch in d[k] (possibly zero or negative): they work on the pivot itself, so that no
+        // lane leaves the fast paths of the square root and the division (their results are never stored)
+        const float pk = __shfl_sync(0xffffffffu, d[k], k);
+        const float dk = xsqrt(pk);
+        const float num = lane > k ? d[k] : dk;
+        const float lk = lane == k ? dk : xdiv(num, make_divisor(dk));
+        d[k] = lk;
+#pragma unroll
+        for (int c = k + 1; c < 32; c++) d[c] = msub<FUSED>(d[c], lk, __shfl_sync(0xffffffffu, lk, c));
+    });
+#pragma unroll
+    for (int c = 0; c < 32; c++)
+        if (c <= lane) T[(c0 + lane) * ldt + c0 + c] = d[c];
+}
+
+template <int M, int NT, bool FUSED>
+__global__ void __launch_bounds__(NT)
+xchol_tile_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int o, long batch_stride) {
+    constexpr int LDT = M + 4;
+    extern __shared__ __align__(16) float xt_smem[];
+    float* T = xt_smem;  // [M][LDT]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* sblk = S + (long)blockIdx.x * batch_stride + (long)o * n + o;
+    float* lblk = L + (long)blockIdx.x * batch_stride + (long)o * n + o;
+    for (int e = tid; e < M * (M / 4); e += NT) {
+        const int row = e / (M / 4), c4 = e % (M / 4);
+        *reinterpret_cast<float4*>(T + row * LDT + 4 * c4) = *(reinterpret_cast<const float4*>(sblk + (long)row * n) + c4);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < M / 32; j++) {
+        const int c0 = 32 * j;
+        if (j > 0) {
+            // (a) rows r0, r0+1 x columns ca, ca+16 of block column j: every element takes k = 0 .. c0-1 in ascending order
+            const int tiles = ((M - c0) / 2) * 16;
+            for (int t = tid; t < tiles; t += NT) {
+                const int cp = t & 15, rp = t >> 4;
+                const int r0 = c0 + 2 * rp, ca = c0 + cp, cb = ca + 16;
+                if (r0 + 1 < ca) continue;  // entirely above the diagonal
+                const float4* A0 = reinterpret_cast<const float4*>(T + r0 * LDT);
+                const float4* A1 = reinterpret_cast<const float4*>(T + (r0 + 1) * LDT);
+                const float4* B0 = reinterpret_cast<const float4*>(T + ca * LDT);
+                const float4* B1 = reinterpret_cast<const float4*>(T + cb * LDT);
+                float s00 = T[r0 * LDT + ca], s01 = T[r0 * LDT + cb], s10 = T[(r0 + 1) * LDT + ca], s11 = T[(r0 + 1) * LDT + cb];
+                for (int k4 = 0; k4 < c0 / 4; k4++) {
+                    const float4 a0 = A0[k4], a1 = A1[k4], b0 = B0[k4], b1 = B1[k4];
+                    s00 = msub<FUSED>(s00, a0.x, b0.x), s01 = msub<FUSED>(s01, a0.x, b1.x), s10 = msub<FUSED>(s10, a1.x, b0.x), s11 = msub<FUSED>(s11, a1.x, b1.x);
+                    s00 = msub<FUSED>(s00, a0.y, b0.y), s01 = msub<FUSED>(s01, a0.y, b1.y), s10 = msub<FUSED>(s10, a1.y, b0.y), s11 = msub<FUSED>(s11, a1.y, b1.y);
+                    s00 = msub<FUSED>(s00, a0.z, b0.z), s01 = msub<FUSED>(s01, a0.z, b1.z), s10 = msub<FUSED>(s10, a1.z, b0.z), s11 = msub<FUSED>(s11, a1.z, b1.z);
+                    s00 = msub<FUSED>(s00, a0.w, b0.w), s01 = msub<FUSED>(s01, a0.w, b1.w), s10 = msub<FUSED>(s10, a1.w, b0.w), s11 = msub<FUSED>(s11, a1.w, b1.w);
+                }
+                if (r0 >= ca) T[r0 * LDT + ca] = s00;
+                if (r0 >= cb) T[r0 * LDT + cb] = s01;
+                if (r0 + 1 >= ca) T[(r0 + 1) * LDT + ca] = s10;
+                if (r0 + 1 >= cb) T[(r0 + 1) * LDT + cb] = s11;
+            }
+            __syncthreads();
+        }
+        // (b) the diagonal block, inside one warp
+        if (warp == 0) xchol32<FUSED>(T, LDT, c0, lane);
+        __syncthreads();
+        // (c) rows below, one thread per row: x_c = (x_c - sum_{m < c, ascending} x_m l_cm) / l_cc
+        if (tid < M - c0 - 32) {
+            float* xrow = T + (c0 + 32 + tid) * LDT + c0;
+            float x[32];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const float4 v = reinterpret_cast<const float4*>(xrow)[q];
+                x[4 * q] = v.x, x[4 * q + 1] = v.y, x[4 * q + 2] = v.z, x[4 * q + 3] = v.w;
+            }
+            static_for<0, 32>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                const float4* lrow = reinterpret_cast<const float4*>(T + (c0 + c) * LDT + c0);
+                float acc = x[c];
+                static_for<0, c / 4 + 1>([&](auto qc) {
+                    constexpr int q = decltype(qc)::value;
+                    const float4 lv = lrow[q];
+                    if constexpr (4 * q < c) acc = msub<FUSED>(acc, x[4 * q], lv.x);
+                    if constexpr (4 * q + 1 < c) acc = msub<FUSED>(acc, x[4 * q + 1], lv.y);
+                    if constexpr (4 * q + 2 < c) acc = msub<FUSED>(acc, x[4 * q + 2], lv.z);
+                    if constexpr (4 * q + 3 < c) acc = msub<FUSED>(acc, x[4 * q + 3], lv.w);
+                    if constexpr (4 * q == (c & ~3)) {
+                        const float dd = (c & 3) == 0 ? lv.x : ((c & 3) == 1 ? lv.y : ((c & 3) == 2 ? lv.z : lv.w));
+                        x[c] = xdiv(acc, dd);
+                    }
+                });
+            });
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                reinterpret_cast<float4*>(xrow)[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < M * (M / 4); e += NT) {
+        const int row = e / (M / 4), c4 = e % (M / 4);
+        float4 v = *reinterpret_cast<const float4*>(T + row * LDT + 4 * c4);
+        if (4 * c4 > row) v.x = 0.0f;
+        if (4 * c4 + 1 > row) v.y = 0.0f;
+        if (4 * c4 + 2 > row) v.z = 0.0f;
+        if (4 * c4 + 3 > row) v.w = 0.0f;
+        *(reinterpret_cast<float4*>(lblk + (long)row * n) + c4) = v;
+    }
+}
+
+// M x M diagonal block at (o, o) of every matrix of the batch (row stride n, matrix stride n * n); n == M, o == 0: a
+// batch of M x M matrices
+template <int M, int NT, bool FUSED>
+static cudaError_t launch_xchol_tile(const float* S, float* L, int n, int o, long batch, cudaStream_t st) {
+    constexpr size_t smem = (size_t)M * (M + 4) * 4;
+    auto kern = xchol_tile_kernel<M, NT, FUSED>;
+    cudaError_t e = ensure_dynamic_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    for (long b0 = 0; b0 < batch; b0 += 1 << 20) {
+        const long cnt = std::min<long>(batch - b0, 1 << 20);
+        kern<<<(unsigned)cnt, NT, smem, st>>>(S + b0 * (long)n * n, L + b0 * (long)n * n, n, o, (long)n * n);
+        count_launch();
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t cholesky_tile_exact(const float* S, float* L, int m, int n, int o, long batch, int fused, cudaStream_t st) {
+    if (m == 64) {
+        // measured (batch 98304): 128 threads per matrix 49.9 M fact/s, 64 threads 41.9 M, register kernel 36.2 M
+        if (option(HLSD_OPT_CHOL_TILE) == 2)
+            return fused ? launch_xchol_tile<64, 64, true>(S, L, n, o, batch, st) : launch_xchol_tile<64, 64, false>(S, L, n, o, batch, st);
+        return fused ? launch_xchol_tile<64, 128, true>(S, L, n, o, batch, st) : launch_xchol_tile<64, 128, false>(S, L, n, o, batch, st);
+    }
+    if (m == 128) return fused ? launch_xchol_tile<128, 256, true>(S, L, n, o, batch, st) : launch_xchol_tile<128, 256, false>(S, L, n, o, batch, st);
+    return cudaErrorNotSupported;
+}
+
 struct XUpdSmem {
     static constexpr int LDK = XR + 4;                 // row stride of the transposed operand tiles [k][row]
     static constexpr int kOp = XB * LDK;
@@ -260,7 +419,12 @@ cudaError_t cholesky_blocked_exact(const float* A, float* L, int n, long batch, 
     for (int q = 0; q < panels; q++) {
         const int o = q * XB;
         const float* src = (q == 0) ? A : L;  // where the not yet factored part currently lives
-        if ((e = chol_diag_exact(src, L, n, o, batch, st)) != cudaSuccess) return e;
+        {
+            ProfScope ps(HLSD_PROF_DIAG, st);
+            e = option(HLSD_OPT_CHOL_TILE) == 1 ? chol_diag_exact(src, L, n, o, batch, st)
+                                                : cholesky_tile_exact(src, L, XB, n, o, batch, 0, st);
+        }
+        if (e != cudaSuccess) return e;
         const int below = n - o - XB;
         if (below > 0) {
             {

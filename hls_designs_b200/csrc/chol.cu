@@ -593,7 +593,11 @@ static cudaError_t launch_group(const float* A, float* L, int n, long batch, cud
 template <int VARIANT, bool FUSED>
 static cudaError_t chol_dispatch(const float* A, float* L, int n, long batch, int path, cudaStream_t st) {
     const bool aligned = (((uintptr_t)A | (uintptr_t)L) & 15) == 0;
-    // 128 x 128, right-looking designs: the register-tiled CTA-per-matrix kernel (blocked.cu, exact mode)
+    // 64 x 64 and 128 x 128, right-looking designs: the shared-memory tile kernel blocked by 32 columns (blocked_exact.cu);
+    // HLSD_OPT_CHOL_TILE = 1: the register kernels (N = 128: the register-tiled CTA-per-matrix kernel of blocked.cu)
+    if (VARIANT == 0 && aligned && (n == 64 || n == 128) && (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM) &&
+        option(HLSD_OPT_CHOL_TILE) != 1)
+        return cholesky_tile_exact(A, L, n, n, 0, batch, FUSED, st);
     if (VARIANT == 0 && n == 128 && (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM)) return cholesky128_exact(A, L, batch, FUSED, st);
     if (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM) {
         if (aligned && n == 4) return launch_tpm<4, VARIANT, FUSED>(A, L, batch, st);

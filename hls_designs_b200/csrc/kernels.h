@@ -47,6 +47,10 @@ cudaError_t qr_exact(const float* A, float* Q, float* R, int rows, int cols, lon
 // on the tcgen05 tensor cores (use_tensor == 1).  cudaErrorNotSupported when the size is not served.
 cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int use_tensor, cudaStream_t st);
 
+// Bit-identical Cholesky (right-looking designs) of the m x m (m = 64, 128) diagonal block at (o, o) of matrices with row
+// stride n, held in shared memory and blocked by 32 columns (blocked_exact.cu); n == m, o == 0: a batch of m x m matrices.
+cudaError_t cholesky_tile_exact(const float* S, float* L, int m, int n, int o, long batch, int fused, cudaStream_t st);
+
 // Bit-identical Cholesky (right-looking designs) of 128 x 128 matrices, register-tiled, one CTA per matrix.
 cudaError_t cholesky128_exact(const float* A, float* L, long batch, int fused, cudaStream_t st);
 

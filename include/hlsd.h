@@ -147,6 +147,9 @@ const char* hlsd_version(void);
                                    of {free-running warps, one CTA-wide barrier per step}                             */
 #define HLSD_OPT_QR_THREADS 5   /* QR 64x64 / 128x128: 0 = one set of threads does the R and the Q work (default),
                                    1 = separate R and Q threads (round 1)                                            */
+#define HLSD_OPT_CHOL_TILE 6    /* exact Cholesky 64 / 128 (right-looking designs): 0 = shared-memory tile kernel blocked by
+                                   32 columns (default), 1 = the register kernels of round 1, 2 = tile kernel with 64
+                                   instead of 128 threads per 64x64 matrix                                             */
 #define HLSD_OPT_COUNT 8
 int hlsd_set_option(int option, int value);
 

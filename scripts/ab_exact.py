@@ -22,9 +22,9 @@ CASES = {
     # name: (kind, n, [(label, {option: value}, fused)])
     "chol32": ("chol", 32, [("dense6", {}, False), ("packed12", {"chol_slab": 1}, False), ("packed8", {"chol_slab": 2}, False),
                             ("dense6+lockstep", {"lockstep": 1}, False), ("dense6+fused", {}, True)]),
-    "chol64": ("chol", 64, [("packed16", {}, False), ("dense12", {"chol_slab": 1}, False), ("packed16+lockstep", {"lockstep": 1}, False),
-                            ("packed16+fused", {}, True)]),
-    "chol128": ("chol", 128, [("default", {}, False), ("fused", {}, True)]),
+    "chol64": ("chol", 64, [("tile128", {}, False), ("tile64", {"chol_tile": 2}, False), ("regs packed16", {"chol_tile": 1}, False),
+                            ("regs dense12", {"chol_tile": 1, "chol_slab": 1}, False), ("tile128+fused", {}, True)]),
+    "chol128": ("chol", 128, [("tile", {}, False), ("regs (blk_diag)", {"chol_tile": 1}, False), ("tile+fused", {}, True)]),
     "lu8": ("lu", 8, [("default", {}, False)]),
     "lu16": ("lu", 16, [("default", {}, False), ("fused", {}, True)]),
     "lu32": ("lu", 32, [("lane", {}, False), ("regs", {"lu32_kernel": 1}, False), ("lane+fused", {}, True)]),
