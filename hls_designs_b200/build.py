@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libhlsd.so")
-SOURCES = ["chol.cu", "lu.cu", "qr.cu", "blocked.cu", "blocked_exact.cu", "selftest.cu", "cabi.cu"]
+SOURCES = ["chol.cu", "lu.cu", "qr.cu", "blocked.cu", "lu_crout.cu", "blocked_exact.cu", "selftest.cu", "cabi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xptxas", "-v", "--expt-relaxed-constexpr"]

@@ -34,79 +34,12 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "tc.cuh"
 
 namespace hlsd {
 
-constexpr int NB = 128;  // panel width = MMA tile edge
 constexpr int kDiagSmem = NB * (NB + 1) * 4;  // dynamic shared memory of blk_diag_kernel
 
-// ------------------------------------------------------------------------------------------------
-// tcgen05 / TMEM wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrive on `bar` when all tcgen05.mma issued so far by this thread have completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100):
-//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
-//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B) | [46,48) version = 1 | [61,64) layout = 2
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, M = 128, N = 128
-constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
 
 // ------------------------------------------------------------------------------------------------
 // Zero the blocks strictly above the block diagonal of L (nothing else ever writes them).  The
@@ -361,7 +294,8 @@ __device__ __forceinline__ void inv32(float* T, float* Dn, const float* rd, int 
 
 template <bool INV_ONLY>
 __global__ void __launch_bounds__(256, 2)
-blk_diag2_kernel(const float* __restrict__ S, float* __restrict__ L, float* __restrict__ W, int n, int o) {
+blk_diag2_kernel(const float* __restrict__ S, float* __restrict__ L, float* __restrict__ W, int n, int o,
+                 const int* __restrict__ rowmap = nullptr) {
     constexpr int LDT = Diag2::LDT, LDN = Diag2::LDN, SH = Diag2::SH;
     extern __shared__ __align__(16) float d2_smem[];
     float* T = d2_smem;
@@ -371,9 +305,12 @@ blk_diag2_kernel(const float* __restrict__ S, float* __restrict__ L, float* __re
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* sblk = S + (long)blockIdx.x * n * n + (long)o * n + o;  // S = A for block column 0, L afterwards
     float* blk = L + (long)blockIdx.x * n * n + (long)o * n + o;
+    // rowmap (blocked LU, lu_crout.cu): row r of the block is row rowmap[o + r] of the matrix S (rows are never moved there)
+    const int* rmap = rowmap ? rowmap + (long)blockIdx.x * n + o : nullptr;
     for (int e = tid; e < NB * (NB / 4); e += 256) {
         const int row = e >> 5, c4 = e & 31;
-        *reinterpret_cast<float4*>(T + row * LDT + 4 * c4) = *(reinterpret_cast<const float4*>(sblk + (long)row * n) + c4);
+        const float* srow = rmap ? S + (long)blockIdx.x * n * n + (long)rmap[row] * n + o : sblk + (long)row * n;
+        *reinterpret_cast<float4*>(T + row * LDT + 4 * c4) = *(reinterpret_cast<const float4*>(srow) + c4);
     }
     if (INV_ONLY && tid < NB) rdiag[tid] = 1.0f;
     __syncthreads();
@@ -525,39 +462,6 @@ blk_diag2_kernel(const float* __restrict__ S, float* __restrict__ L, float* __re
 // ------------------------------------------------------------------------------------------------
 // tensor-core tile kernel
 // ------------------------------------------------------------------------------------------------
-struct MmaSmem {
-    // per 32-wide K chunk an operand tile is 128 rows x 32 k fp32 = one swizzle atom [128 rows][128 B].
-    // raw fp32 tiles (2 stages x {A, B}) are filled by cp.async and double as the tf32 "hi" operands:
-    // the tensor core reads only the upper 19 bits of each 32-bit container, i.e. hi = trunc_tf32(x);
-    // the "lo" tiles hold rna_tf32(x - hi) computed by the threads.
-    static constexpr int kChunkK = 32;
-    static constexpr int kTileBytes = 128 * kChunkK * 4;
-    static constexpr int kStages = 1;  // raw stages: 1 -> 64 KB per CTA (3 CTAs/SM), 2 -> 96 KB (2 CTAs/SM)
-    static constexpr int kRawA = 0, kRawB = kStages * kTileBytes;      // [stage] each
-    static constexpr int kLoA = 2 * kStages * kTileBytes, kLoB = kLoA + kTileBytes;
-    static constexpr int kBar = kLoB + kTileBytes;
-    static constexpr int kTmemPtr = kBar + 8;
-    static constexpr int kTotal = kBar + 16 + 1024;  // + slack for the 1024-byte alignment of the tiles
-};
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// lo part of a float4 sitting in a raw tile: x - trunc_tf32(x), rounded to tf32
-__device__ __forceinline__ float4 lo_of(float4 v) {
-    float4 l;
-    l.x = to_tf32(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
-    l.y = to_tf32(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
-    l.z = to_tf32(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
-    l.w = to_tf32(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
-    return l;
-}
 
 // TRSM tiles of the blocked Cholesky: L[r][q] = X[r][q] * W^T.  grid: (row blocks below the diagonal block, batch)
 __global__ void __launch_bounds__(256, MmaSmem::kStages == 1 ? 3 : 2)
@@ -1400,7 +1304,18 @@ lu_transpose_kernel(float* __restrict__ Wk, float* __restrict__ T, int n, int o)
 
 constexpr int kUnswapThreads = 1024;  // the gather / scatter of the touched rows is latency bound: more loads in flight
 
-cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long batch, cudaStream_t st) {
+// W = inv(L11) for the Crout LU (lu_crout.cu): L11 = rows posmap[o .. o+127] of M2, columns o .. o+127 (unit lower)
+cudaError_t lu_inverse_l11(const float* M2, const int* posmap, float* W, int n, int o, long batch, cudaStream_t st) {
+    cudaError_t e = ensure_dynamic_smem(blk_diag2_kernel<true>, Diag2::kBytes);
+    if (e != cudaSuccess) return e;
+    blk_diag2_kernel<true><<<(unsigned)batch, 256, Diag2::kBytes, st>>>(M2, W, W, n, o, posmap);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// Round-1/2 right-looking form (one rank-128 tensor update per panel, rows exchanged physically): kept while the Crout
+// form (lu_crout.cu) is being measured against it (HLSD_OPT_LU_TENSOR = 1).
+cudaError_t lu_blocked_rl(const float* A, float* L, float* U, int* P, int n, long batch, cudaStream_t st) {
     if (n % NB != 0 || n < 2 * NB || n > 1024) return cudaErrorNotSupported;
     if ((((uintptr_t)A | (uintptr_t)L | (uintptr_t)U) & 15) != 0) return cudaErrorNotSupported;
     if (batch == 0) return cudaSuccess;
