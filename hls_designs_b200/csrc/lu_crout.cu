@@ -386,6 +386,7 @@ struct PCand {
     unsigned key;
     int pos;
 };
+constexpr int kXposeWarpBytes = 32 * 36 * 4;  // dynamic shared memory of lu_cpanel_kernel per warp
 
 __global__ void __launch_bounds__(1024, 1)
 lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restrict__ U, int* __restrict__ P,
@@ -395,6 +396,7 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
     __shared__ __align__(16) float prow[32][36];     // pivot rows of the sub-panel: multipliers | U11
     __shared__ int tw[32];                           // thread that won step kk
     __shared__ __align__(16) float ublk[32][100];    // the sub-panel's U rows in the remaining panel columns (<= 96)
+    extern __shared__ __align__(16) float xpose[];   // [warps][32][36]: per-warp transposition stage of the M2 stores
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int nwarps = blockDim.x >> 5;
     const int R = n - o;
@@ -421,13 +423,11 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
             const unsigned wmax = __reduce_max_sync(kFull, key);
             const unsigned cpos = (key == wmax && wmax != 0u) ? (unsigned)mypos : 0x7fffffffu;
             const unsigned wpos = __reduce_min_sync(kFull, cpos);
-            if (wmax != 0u && cpos == wpos) {
+            if (lane == 0) cand[par][warp] = PCand{wmax, (int)wpos};  // (no candidate: key 0, position 0x7fffffff)
+            if (cpos == wpos && wmax != 0u) {
                 float4* dst = reinterpret_cast<float4*>(slot[par][warp]);
 #pragma unroll
                 for (int q = kk / 4; q < 8; q++) dst[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
-                cand[par][warp] = PCand{wmax, (int)wpos};
-            } else if (wmax == 0u && lane == 0) {
-                cand[par][warp] = PCand{0u, 0x7fffffff};
             }
             __syncthreads();
             const PCand c = lane < nwarps ? cand[par][lane] : PCand{0u, 0x7fffffff};
@@ -447,7 +447,12 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
                 mypos = gp;
             }
             if (mypos > k) {
-                const float l = a[kk] / urow[kk];
+                // quotient = reciprocal (MUFU) times numerator, corrected once with the exact residual
+                const float piv = urow[kk];
+                float r;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(piv));
+                const float l0 = a[kk] * r;
+                const float l = fmaf(fmaf(-piv, l0, a[kk]), r, l0);
                 a[kk] = l;
                 const float4* u4 = reinterpret_cast<const float4*>(urow);
                 static_for<(kk + 1) / 4, 8>([&](auto qc) {
@@ -460,32 +465,58 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
                 });
             }
         });
-        if (live) {
-            float4* dst = reinterpret_cast<float4*>(M2 + b * n * n + (long)phys * n + o + cs);
+        {
+            // M2[physical row][o + cs .. + 31] = the row's 32 registers: transposed through shared memory so that one
+            // store instruction writes four complete 128-byte rows instead of a 16-byte piece of thirty-two
+            float* xp = xpose + warp * (32 * 36);
+            float4* mine = reinterpret_cast<float4*>(xp + lane * 36);
 #pragma unroll
-            for (int q = 0; q < 8; q++) dst[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+            for (int q = 0; q < 8; q++) mine[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+            __syncwarp();
+            float* m2b = M2 + b * n * n + o + cs + 4 * (lane & 7);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int row = 4 * i + (lane >> 3);
+                const int prow_phys = __shfl_sync(kFull, phys, row);
+                const float4 v = *reinterpret_cast<const float4*>(xp + row * 36 + 4 * (lane & 7));
+                if (warp * 32 + row < R) *reinterpret_cast<float4*>(m2b + (long)prow_phys * n) = v;
+            }
         }
         __syncthreads();  // prow and tw are complete
         const int rem0 = cs + 32, nrem = NB - rem0;  // panel columns right of the sub-panel
         if (nrem > 0) {
             // the new pivot rows in those columns (as they are now: updated by the earlier sub-panels)
             const float* pwb = PWT + b * n * NB;
-            for (int e = t; e < 32 * nrem; e += blockDim.x) {
-                const int kk = e & 31, c = e >> 5;
-                ublk[kk][c] = pwb[(long)(rem0 + c) * n + tw[kk]];
+            {
+                const int row_t = tw[lane];  // e & 31 == lane for every element e of this thread (blockDim % 32 == 0)
+                for (int e0 = t; e0 < 32 * nrem; e0 += 4 * blockDim.x) {
+                    float g[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int e = e0 + i * blockDim.x;
+                        if (e < 32 * nrem) g[i] = pwb[(long)(rem0 + (e >> 5)) * n + row_t];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int e = e0 + i * blockDim.x;
+                        if (e < 32 * nrem) ublk[lane][e >> 5] = g[i];
+                    }
+                }
             }
             __syncthreads();
-            // forward substitution with the unit-lower 32 x 32 block (multipliers of the pivot rows): thread = column
-            if (t < nrem) {
+            // forward substitution with the unit-lower 32 x 32 block (multipliers of the pivot rows): eight lanes per
+            // column, each summing the terms j = part, part + 8, ... of a row, folded by shuffles (nrem % 4 == 0: the
+            // four columns of a warp are all inside or all outside)
+            for (int c = t >> 3; c < nrem; c += blockDim.x >> 3) {
+                const int part = t & 7;
                 for (int kk = 1; kk < 32; kk++) {
-                    float s0 = ublk[kk][t], s1 = 0.0f;
-                    int j = 0;
-                    for (; j + 1 < kk; j += 2) {
-                        s0 = fmaf(-prow[kk][j], ublk[j][t], s0);
-                        s1 = fmaf(-prow[kk][j + 1], ublk[j + 1][t], s1);
-                    }
-                    if (j < kk) s0 = fmaf(-prow[kk][j], ublk[j][t], s0);
-                    ublk[kk][t] = s0 + s1;
+                    float s0 = 0.0f;
+                    for (int j = part; j < kk; j += 8) s0 = fmaf(prow[kk][j], ublk[j][c], s0);
+                    s0 += __shfl_xor_sync(kFull, s0, 1);
+                    s0 += __shfl_xor_sync(kFull, s0, 2);
+                    s0 += __shfl_xor_sync(kFull, s0, 4);
+                    if (part == 0) ublk[kk][c] -= s0;
+                    __syncwarp();
                 }
             }
             __syncthreads();
@@ -524,27 +555,19 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
 // L in the reference's layout from M2: L[i][k] = multiplier, at step k, of the row that sat at position i right after
 // step k's exchange (lu_v1.1/model4x4/lu.cpp:55-63 exchanges columns >= id only, so a multiplier stays at the position
 // where it was computed).  Per (panel, matrix): positions the panel's 128 exchanges never touch keep their occupant
-// for the whole panel and are copied row by row; the touched positions (<= 256: o..o+127 and the distinct pivots
-// below) are staged in shared memory, one warp replays the exchanges on an occupancy vector and records it per step,
-// and every output row then picks, per column, the staged row that sat there at that step.
-// grid: (panels, batch), 512 threads
+// for the whole panel and are copied row by row.  For the touched positions ("slots": o..o+127 and the distinct pivots
+// below, <= 256) one thread replays the exchanges on an occupancy vector and records, per step j, which row was put
+// into the pivot's slot q_j; a slot's occupant at column j is then the value of the last such event <= j that names
+// it (a ballot and a shuffle per 32 columns), and every output element is read straight from that row of M2 - mostly
+// one row per output row, so the loads stay coalesced.  No staging tile: ~6 KB of shared memory, many CTAs per SM.
+// grid: (panels, batch), 256 threads
 // ------------------------------------------------------------------------------------------------
-struct AsmSmem {
-    static constexpr int kOccLd = 260;  // bytes per step row of the occupancy history (odd word stride: conflict-free)
-    static constexpr int kTile = 2 * NB * NB * 4;
-    static constexpr int kOcc = NB * kOccLd;
-    static constexpr int kTotal = kTile + kOcc;
-};
-
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(256)
 lu_assemble_l_kernel(const float* __restrict__ M2, float* __restrict__ L, const int* __restrict__ P,
                      const int* __restrict__ hist, int n, int panels) {
-    extern __shared__ __align__(16) unsigned char asm_smem[];
-    float* tile = reinterpret_cast<float*>(asm_smem);                 // [<= 256 slots][128]
-    unsigned char* occh = asm_smem + AsmSmem::kTile;                  // [128 steps][kOccLd]: slot -> staged row
-    __shared__ int piv[NB], pslot[NB], spos[2 * NB];
+    __shared__ int piv[NB], qslot[NB], spos[2 * NB], srow[2 * NB];
     __shared__ short slot_of[1024];
-    __shared__ __align__(16) unsigned char occ[2 * NB];
+    __shared__ unsigned char occ[2 * NB], evval[NB];
     __shared__ int s_cnt;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int p = blockIdx.x, o = p * NB;
@@ -553,7 +576,7 @@ lu_assemble_l_kernel(const float* __restrict__ M2, float* __restrict__ L, const 
     const float* m2 = M2 + b * n * n + o;
     float* lo = L + b * n * n + o;
     if (t < NB) piv[t] = P[b * n + o + t];
-    for (int i = t; i < n; i += 512) slot_of[i] = -1;
+    for (int i = t; i < n; i += 256) slot_of[i] = -1;
     __syncthreads();
     if (t < NB && piv[t] >= o + NB) slot_of[piv[t]] = -2;  // marked
     __syncthreads();
@@ -575,36 +598,24 @@ lu_assemble_l_kernel(const float* __restrict__ M2, float* __restrict__ L, const 
     }
     __syncthreads();
     const int cnt = s_cnt;
-    if (t < NB) pslot[t] = piv[t] < o + NB ? piv[t] - o : slot_of[piv[t]];
-    for (int s = t; s < cnt; s += 512) occ[s] = (unsigned char)s;
-    // stage the touched rows (as they lie when the panel starts); four rows per warp pass for memory-level parallelism
-    for (int s0 = warp * 4; s0 < cnt; s0 += 64) {
-        float4 v[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            if (s0 + i < cnt) v[i] = __ldg(reinterpret_cast<const float4*>(m2 + (long)pm[spos[s0 + i]] * n) + lane);
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            if (s0 + i < cnt) *reinterpret_cast<float4*>(tile + (s0 + i) * NB + 4 * lane) = v[i];
+    if (t < NB) qslot[t] = piv[t] < o + NB ? piv[t] - o : slot_of[piv[t]];
+    for (int s = t; s < cnt; s += 256) {
+        occ[s] = (unsigned char)s;
+        srow[s] = pm[spos[s]];  // physical row sitting at slot s when the panel starts
     }
     __syncthreads();
-    if (warp == 0) {
-        // replay the 128 exchanges; after step j, occh[j][s] = staged row sitting at slot s
+    if (t == 0) {
+        // replay: step j exchanges the occupants of slot j and slot q_j; evval[j] = what q_j receives
         for (int j = 0; j < NB; j++) {
-            if (lane == 0) {
-                const int s2 = pslot[j];
-                const unsigned char x = occ[j];
-                occ[j] = occ[s2];
-                occ[s2] = x;
-            }
-            __syncwarp();
-            for (int s = lane * 4; s < cnt; s += 128)
-                *reinterpret_cast<uint32_t*>(occh + j * AsmSmem::kOccLd + s) = *reinterpret_cast<const uint32_t*>(occ + s);
-            __syncwarp();
+            const int q = qslot[j];
+            const unsigned char x = occ[j], y = occ[q];
+            occ[j] = y;
+            occ[q] = x;
+            evval[j] = x;
         }
-    } else {
+    } else if (warp > 0) {
         // meanwhile: positions the panel never touches keep their row for all 128 steps
-        for (int i0 = o + NB + (warp - 1) * 4; i0 < n; i0 += 60) {
+        for (int i0 = o + NB + (warp - 1) * 4; i0 < n; i0 += 28) {
             float4 v[4];
             bool w[4];
 #pragma unroll
@@ -618,17 +629,25 @@ lu_assemble_l_kernel(const float* __restrict__ M2, float* __restrict__ L, const 
         }
     }
     __syncthreads();
-    for (int s = warp; s < cnt; s += 16) {
+    for (int s = warp; s < cnt; s += 8) {
         const int pos = spos[s];
+        int carry = s;  // occupant before the first event: the row that sat here when the panel started
         float v[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int j = lane + 32 * i;  // column o + j
+        for (int g = 0; g < 4; g++) {
+            const int j = 32 * g + lane;
+            const bool flag = qslot[j] == s;
+            const int val = evval[j];
+            const unsigned bal = __ballot_sync(0xffffffffu, flag);
+            const unsigned m = bal & (0xffffffffu >> (31 - lane));  // events at columns <= j of this group
+            const int from = __shfl_sync(0xffffffffu, val, m ? 31 - __clz(m) : 0);
+            const int here = m ? from : carry;
+            if (bal) carry = __shfl_sync(0xffffffffu, val, 31 - __clz(bal));
             const int k = o + j;
-            v[i] = pos > k ? tile[occh[j * AsmSmem::kOccLd + s] * NB + j] : (pos == k ? 1.0f : 0.0f);
+            v[g] = pos > k ? __ldg(m2 + (long)srow[here] * n + j) : (pos == k ? 1.0f : 0.0f);
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) __stcs(lo + (long)pos * n + lane + 32 * i, v[i]);
+        for (int g = 0; g < 4; g++) __stcs(lo + (long)pos * n + 32 * g + lane, v[g]);
     }
 }
 
@@ -666,7 +685,8 @@ static cudaError_t lu_crout_slice(const float* A, float* L, float* U, int* P, in
         }
         {
             ProfScope ps(HLSD_PROF_PANEL, st);
-            lu_cpanel_kernel<<<nb, std::max(256, n - o), 0, st>>>(PWT, M2, U, P, pm(p), pm(p + 1), n, o);
+            const int pthreads = std::max(256, n - o);
+            lu_cpanel_kernel<<<nb, pthreads, (size_t)(pthreads / 32) * kXposeWarpBytes, st>>>(PWT, M2, U, P, pm(p), pm(p + 1), n, o);
             count_launch();
         }
         if (ct == 0) break;
@@ -688,7 +708,7 @@ static cudaError_t lu_crout_slice(const float* A, float* L, float* U, int* P, in
     }
     {
         ProfScope ps(HLSD_PROF_PERMUTE, st);
-        lu_assemble_l_kernel<<<dim3(panels, nb), 512, AsmSmem::kTotal, st>>>(M2, L, P, hist, n, panels);
+        lu_assemble_l_kernel<<<dim3(panels, nb), 256, 0, st>>>(M2, L, P, hist, n, panels);
         count_launch();
     }
     return cudaGetLastError();
@@ -702,7 +722,7 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
     if ((e = ensure_dynamic_smem(lu_ll_kernel<LL_COL>, LlSmem::kTotal)) != cudaSuccess) return e;
     if ((e = ensure_dynamic_smem(lu_ll_kernel<LL_ROW>, LlSmem::kTotal)) != cudaSuccess) return e;
     if ((e = ensure_dynamic_smem(lu_trsm_kernel, MmaSmem::kTotal)) != cudaSuccess) return e;
-    if ((e = ensure_dynamic_smem(lu_assemble_l_kernel, AsmSmem::kTotal)) != cudaSuccess) return e;
+    if ((e = ensure_dynamic_smem(lu_cpanel_kernel, 32 * kXposeWarpBytes)) != cudaSuccess) return e;
     const long nn = (long)n * n;
     const int panels = n / NB;
     // workspace per matrix: M2, UT (n x n), PWT, T0 (n x 128), W (128 x 128), posmap history; the batch is walked in
