@@ -388,46 +388,69 @@ struct PCand {
 };
 constexpr int kXposeWarpBytes = 32 * 36 * 4;  // dynamic shared memory of lu_cpanel_kernel per warp
 
-__global__ void __launch_bounds__(1024, 1)
+// RPT = rows per thread (thread t holds the rows at positions o + t and o + t + blockDim.x): the per-column work that
+// does not depend on the row count - key reduction, publication, the barrier, the winner test - is paid once per
+// thread, so two rows per thread nearly halve the instructions of the column loop, and the U rows read from shared
+// memory in the rank-32 update serve eight instead of four multiply-adds.
+template <int RPT>
+__global__ void __launch_bounds__(1024 / RPT, 1)
 lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restrict__ U, int* __restrict__ P,
                  const int* __restrict__ pm_in, int* __restrict__ pm_out, int n, int o) {
     __shared__ __align__(16) float slot[2][32][32];  // speculative pivot rows, one per warp
     __shared__ PCand cand[2][32];
     __shared__ __align__(16) float prow[32][36];     // pivot rows of the sub-panel: multipliers | U11
-    __shared__ int tw[32];                           // thread that won step kk
+    __shared__ int tw[32];                           // row (index into PWT) that won step kk
     __shared__ __align__(16) float ublk[32][100];    // the sub-panel's U rows in the remaining panel columns (<= 96)
     extern __shared__ __align__(16) float xpose[];   // [warps][32][36]: per-warp transposition stage of the M2 stores
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int nwarps = blockDim.x >> 5;
+    const int T = blockDim.x, nwarps = T >> 5;
     const int R = n - o;
-    const bool live = t < R;
     const long b = blockIdx.x;
-    float* pw = PWT + b * n * NB + t;  // element (c): pw[c * n]
-    const int phys = live ? pm_in[b * n + o + t] : 0;
-    int mypos = live ? o + t : -1;
+    float* pwb = PWT + b * n * NB;  // element (c, row): pwb[c * n + row]
+    int phys[RPT], mypos[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; i++) {
+        const int ri = t + i * T;
+        phys[i] = ri < R ? pm_in[b * n + o + ri] : 0;
+        mypos[i] = ri < R ? o + ri : -1;
+    }
     constexpr unsigned kFull = 0xffffffffu;
     for (int sp = 0; sp < 4; sp++) {
         const int cs = 32 * sp;
-        float a[32];
+        float a[RPT][32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) a[j] = live ? pw[(long)(cs + j) * n] : 0.0f;
+        for (int i = 0; i < RPT; i++)
+#pragma unroll
+            for (int j = 0; j < 32; j++) a[i][j] = t + i * T < R ? pwb[(long)(cs + j) * n + t + i * T] : 0.0f;
         static_for<0, 32>([&](auto kkc) {
             constexpr int kk = decltype(kkc)::value;
             constexpr int par = kk & 1;
             const int k = o + cs + kk;
-            unsigned key = 0;
-            if (mypos >= k) {
-                const float v = fabsf(a[kk]);
-                key = (v != v) ? (mypos == k ? 0x7f800001u : 0u) : __float_as_uint(v) + 1u;
+            unsigned kb = 0;
+            int pb = 0x7fffffff;
+#pragma unroll
+            for (int i = 0; i < RPT; i++) {
+                unsigned key = 0;
+                if (mypos[i] >= k) {
+                    const float v = fabsf(a[i][kk]);
+                    key = (v != v) ? (mypos[i] == k ? 0x7f800001u : 0u) : __float_as_uint(v) + 1u;
+                }
+                if (key > kb || (key == kb && key != 0u && mypos[i] < pb)) kb = key, pb = mypos[i];
             }
-            const unsigned wmax = __reduce_max_sync(kFull, key);
-            const unsigned cpos = (key == wmax && wmax != 0u) ? (unsigned)mypos : 0x7fffffffu;
+            const unsigned wmax = __reduce_max_sync(kFull, kb);
+            const unsigned cpos = (kb == wmax && wmax != 0u) ? (unsigned)pb : 0x7fffffffu;
             const unsigned wpos = __reduce_min_sync(kFull, cpos);
             if (lane == 0) cand[par][warp] = PCand{wmax, (int)wpos};  // (no candidate: key 0, position 0x7fffffff)
             if (cpos == wpos && wmax != 0u) {
                 float4* dst = reinterpret_cast<float4*>(slot[par][warp]);
+                if (RPT == 2 && mypos[RPT - 1] == (int)wpos) {
 #pragma unroll
-                for (int q = kk / 4; q < 8; q++) dst[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+                    for (int q = kk / 4; q < 8; q++)
+                        dst[q] = make_float4(a[RPT - 1][4 * q], a[RPT - 1][4 * q + 1], a[RPT - 1][4 * q + 2], a[RPT - 1][4 * q + 3]);
+                } else {
+#pragma unroll
+                    for (int q = kk / 4; q < 8; q++) dst[q] = make_float4(a[0][4 * q], a[0][4 * q + 1], a[0][4 * q + 2], a[0][4 * q + 3]);
+                }
             }
             __syncthreads();
             const PCand c = lane < nwarps ? cand[par][lane] : PCand{0u, 0x7fffffff};
@@ -437,31 +460,48 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
             const int wwin = __ffs(__ballot_sync(kFull, c.key == gmax && c.pos == gp)) - 1;
             const float* urow = slot[par][wwin];
             if (t == 0) P[b * n + k] = gp;
-            if (mypos == gp) {  // this thread's row is the pivot row: it takes position k and retires
-                tw[kk] = t;
-                float4* dst = reinterpret_cast<float4*>(prow[kk]);
+            bool act[RPT];
 #pragma unroll
-                for (int q = 0; q < 8; q++) dst[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
-                mypos = k;
-            } else if (mypos == k) {
-                mypos = gp;
+            for (int i = 0; i < RPT; i++) {
+                if (mypos[i] == gp) {  // this row is the pivot row: it takes position k and retires
+                    tw[kk] = t + i * T;
+                    float4* dst = reinterpret_cast<float4*>(prow[kk]);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) dst[q] = make_float4(a[i][4 * q], a[i][4 * q + 1], a[i][4 * q + 2], a[i][4 * q + 3]);
+                    mypos[i] = k;
+                } else if (mypos[i] == k) {
+                    mypos[i] = gp;
+                }
+                act[i] = mypos[i] > k;
             }
-            if (mypos > k) {
+            bool any = act[0];
+#pragma unroll
+            for (int i = 1; i < RPT; i++) any |= act[i];
+            if (any) {
                 // quotient = reciprocal (MUFU) times numerator, corrected once with the exact residual
                 const float piv = urow[kk];
                 float r;
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(piv));
-                const float l0 = a[kk] * r;
-                const float l = fmaf(fmaf(-piv, l0, a[kk]), r, l0);
-                a[kk] = l;
+                float l[RPT];
+#pragma unroll
+                for (int i = 0; i < RPT; i++) {
+                    const float l0 = a[i][kk] * r;
+                    l[i] = fmaf(fmaf(-piv, l0, a[i][kk]), r, l0);
+                    if (act[i]) a[i][kk] = l[i];
+                }
                 const float4* u4 = reinterpret_cast<const float4*>(urow);
                 static_for<(kk + 1) / 4, 8>([&](auto qc) {
                     constexpr int q = decltype(qc)::value;
                     const float4 u = u4[q];
-                    if constexpr (4 * q > kk) a[4 * q] = fmaf(-l, u.x, a[4 * q]);
-                    if constexpr (4 * q + 1 > kk) a[4 * q + 1] = fmaf(-l, u.y, a[4 * q + 1]);
-                    if constexpr (4 * q + 2 > kk) a[4 * q + 2] = fmaf(-l, u.z, a[4 * q + 2]);
-                    if constexpr (4 * q + 3 > kk) a[4 * q + 3] = fmaf(-l, u.w, a[4 * q + 3]);
+#pragma unroll
+                    for (int i = 0; i < RPT; i++) {
+                        if (act[i]) {
+                            if constexpr (4 * q > kk) a[i][4 * q] = fmaf(-l[i], u.x, a[i][4 * q]);
+                            if constexpr (4 * q + 1 > kk) a[i][4 * q + 1] = fmaf(-l[i], u.y, a[i][4 * q + 1]);
+                            if constexpr (4 * q + 2 > kk) a[i][4 * q + 2] = fmaf(-l[i], u.z, a[i][4 * q + 2]);
+                            if constexpr (4 * q + 3 > kk) a[i][4 * q + 3] = fmaf(-l[i], u.w, a[i][4 * q + 3]);
+                        }
+                    }
                 });
             }
         });
@@ -470,73 +510,120 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
             // store instruction writes four complete 128-byte rows instead of a 16-byte piece of thirty-two
             float* xp = xpose + warp * (32 * 36);
             float4* mine = reinterpret_cast<float4*>(xp + lane * 36);
-#pragma unroll
-            for (int q = 0; q < 8; q++) mine[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
-            __syncwarp();
             float* m2b = M2 + b * n * n + o + cs + 4 * (lane & 7);
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int row = 4 * i + (lane >> 3);
-                const int prow_phys = __shfl_sync(kFull, phys, row);
-                const float4 v = *reinterpret_cast<const float4*>(xp + row * 36 + 4 * (lane & 7));
-                if (warp * 32 + row < R) *reinterpret_cast<float4*>(m2b + (long)prow_phys * n) = v;
+            for (int i = 0; i < RPT; i++) {
+                if (i > 0) __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 8; q++) mine[q] = make_float4(a[i][4 * q], a[i][4 * q + 1], a[i][4 * q + 2], a[i][4 * q + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int g = 0; g < 8; g++) {
+                    const int row = 4 * g + (lane >> 3);
+                    const int row_phys = __shfl_sync(kFull, phys[i], row);
+                    const float4 v = *reinterpret_cast<const float4*>(xp + row * 36 + 4 * (lane & 7));
+                    if (warp * 32 + row + i * T < R) *reinterpret_cast<float4*>(m2b + (long)row_phys * n) = v;
+                }
             }
         }
         __syncthreads();  // prow and tw are complete
         const int rem0 = cs + 32, nrem = NB - rem0;  // panel columns right of the sub-panel
         if (nrem > 0) {
             // the new pivot rows in those columns (as they are now: updated by the earlier sub-panels)
-            const float* pwb = PWT + b * n * NB;
             {
                 const int row_t = tw[lane];  // e & 31 == lane for every element e of this thread (blockDim % 32 == 0)
-                for (int e0 = t; e0 < 32 * nrem; e0 += 4 * blockDim.x) {
+                for (int e0 = t; e0 < 32 * nrem; e0 += 4 * T) {
                     float g[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        const int e = e0 + i * blockDim.x;
+                        const int e = e0 + i * T;
                         if (e < 32 * nrem) g[i] = pwb[(long)(rem0 + (e >> 5)) * n + row_t];
                     }
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        const int e = e0 + i * blockDim.x;
+                        const int e = e0 + i * T;
                         if (e < 32 * nrem) ublk[lane][e >> 5] = g[i];
                     }
                 }
             }
             __syncthreads();
-            // forward substitution with the unit-lower 32 x 32 block (multipliers of the pivot rows): eight lanes per
-            // column, each summing the terms j = part, part + 8, ... of a row, folded by shuffles (nrem % 4 == 0: the
-            // four columns of a warp are all inside or all outside)
-            for (int c = t >> 3; c < nrem; c += blockDim.x >> 3) {
-                const int part = t & 7;
-                for (int kk = 1; kk < 32; kk++) {
-                    float s0 = 0.0f;
-                    for (int j = part; j < kk; j += 8) s0 = fmaf(prow[kk][j], ublk[j][c], s0);
-                    s0 += __shfl_xor_sync(kFull, s0, 1);
-                    s0 += __shfl_xor_sync(kFull, s0, 2);
-                    s0 += __shfl_xor_sync(kFull, s0, 4);
-                    if (part == 0) ublk[kk][c] -= s0;
-                    __syncwarp();
+            // forward substitution with the unit-lower 32 x 32 block (multipliers of the pivot rows): a warp per group of
+            // three columns, lane j = row j of the block with its multipliers in registers; row kk of the result travels by
+            // shuffle, rows below it subtract their multiple of it (right-looking: 32 steps of shuffle + multiply-add)
+            {
+                float lrow[32];
+                {
+                    const float4* src = reinterpret_cast<const float4*>(prow[lane]);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const float4 v = src[q];
+                        lrow[4 * q] = v.x, lrow[4 * q + 1] = v.y, lrow[4 * q + 2] = v.z, lrow[4 * q + 3] = v.w;
+                    }
+                }
+                for (int c0 = 3 * warp; c0 < nrem; c0 += 3 * nwarps) {
+                    float x[3];
+#pragma unroll
+                    for (int e = 0; e < 3; e++) x[e] = c0 + e < nrem ? ublk[lane][c0 + e] : 0.0f;
+#pragma unroll
+                    for (int kk = 0; kk < 31; kk++) {
+#pragma unroll
+                        for (int e = 0; e < 3; e++) {
+                            const float xk = __shfl_sync(kFull, x[e], kk);
+                            if (lane > kk) x[e] = fmaf(-lrow[kk], xk, x[e]);
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 3; e++)
+                        if (c0 + e < nrem) ublk[lane][c0 + e] = x[e];
                 }
             }
             __syncthreads();
-            // rank-32 update of the rows that are not pivot rows yet
-            if (mypos >= o + rem0) {
+            // rank-32 update of the rows that are not pivot rows yet (a thread's retired row is computed along and not stored)
+            bool upd[RPT];
+            bool any = false;
+#pragma unroll
+            for (int i = 0; i < RPT; i++) upd[i] = mypos[i] >= o + rem0, any |= upd[i];
+            if (any) {
+                float v[RPT][4], nx[RPT][4];
+                {
+                    const float* p0 = pwb + (long)rem0 * n + t;
+#pragma unroll
+                    for (int i = 0; i < RPT; i++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) nx[i][e] = p0[(long)e * n + i * T];
+                }
                 for (int c4 = 0; c4 < nrem / 4; c4++) {
-                    float* p0 = pw + (long)(rem0 + 4 * c4) * n;
-                    float v0 = p0[0], v1 = p0[n], v2 = p0[2 * (long)n], v3 = p0[3 * (long)n];
+                    float* p0 = pwb + (long)(rem0 + 4 * c4) * n + t;
+#pragma unroll
+                    for (int i = 0; i < RPT; i++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) v[i][e] = nx[i][e];
+                    if (c4 + 1 < nrem / 4) {  // the next four columns' values, in flight during this group's arithmetic
+#pragma unroll
+                        for (int i = 0; i < RPT; i++)
+#pragma unroll
+                            for (int e = 0; e < 4; e++) nx[i][e] = p0[(long)(4 + e) * n + i * T];
+                    }
 #pragma unroll
                     for (int kk = 0; kk < 32; kk++) {
                         const float4 u = *reinterpret_cast<const float4*>(&ublk[kk][4 * c4]);
-                        v0 = fmaf(-a[kk], u.x, v0), v1 = fmaf(-a[kk], u.y, v1);
-                        v2 = fmaf(-a[kk], u.z, v2), v3 = fmaf(-a[kk], u.w, v3);
+#pragma unroll
+                        for (int i = 0; i < RPT; i++) {
+                            v[i][0] = fmaf(-a[i][kk], u.x, v[i][0]), v[i][1] = fmaf(-a[i][kk], u.y, v[i][1]);
+                            v[i][2] = fmaf(-a[i][kk], u.z, v[i][2]), v[i][3] = fmaf(-a[i][kk], u.w, v[i][3]);
+                        }
                     }
-                    p0[0] = v0, p0[n] = v1, p0[2 * (long)n] = v2, p0[3 * (long)n] = v3;
+#pragma unroll
+                    for (int i = 0; i < RPT; i++)
+                        if (upd[i]) {
+#pragma unroll
+                            for (int e = 0; e < 4; e++) p0[(long)e * n + i * T] = v[i][e];
+                        }
                 }
             }
         }
         // rows o+cs .. o+cs+31 of U inside the panel: zeros | U11 of the sub-panel | its U12
-        for (int e = t; e < 32 * 32; e += blockDim.x) {
+        for (int e = t; e < 32 * 32; e += T) {
             const int kk = e >> 5, q = e & 31;
             float v[4];
 #pragma unroll
@@ -548,7 +635,9 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
         }
         __syncthreads();  // prow, tw, ublk are reused by the next sub-panel
     }
-    if (live) pm_out[b * n + mypos] = phys;
+#pragma unroll
+    for (int i = 0; i < RPT; i++)
+        if (t + i * T < R) pm_out[b * n + mypos[i]] = phys[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -685,8 +774,13 @@ static cudaError_t lu_crout_slice(const float* A, float* L, float* U, int* P, in
         }
         {
             ProfScope ps(HLSD_PROF_PANEL, st);
-            const int pthreads = std::max(256, n - o);
-            lu_cpanel_kernel<<<nb, pthreads, (size_t)(pthreads / 32) * kXposeWarpBytes, st>>>(PWT, M2, U, P, pm(p), pm(p + 1), n, o);
+            if (option(HLSD_OPT_LU_PANEL_ROWS) == 1) {
+                const int pthreads = std::max(256, n - o);
+                lu_cpanel_kernel<1><<<nb, pthreads, (size_t)(pthreads / 32) * kXposeWarpBytes, st>>>(PWT, M2, U, P, pm(p), pm(p + 1), n, o);
+            } else {
+                const int pthreads = std::max(128, (n - o) / 2);
+                lu_cpanel_kernel<2><<<nb, pthreads, (size_t)(pthreads / 32) * kXposeWarpBytes, st>>>(PWT, M2, U, P, pm(p), pm(p + 1), n, o);
+            }
             count_launch();
         }
         if (ct == 0) break;
@@ -722,7 +816,8 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
     if ((e = ensure_dynamic_smem(lu_ll_kernel<LL_COL>, LlSmem::kTotal)) != cudaSuccess) return e;
     if ((e = ensure_dynamic_smem(lu_ll_kernel<LL_ROW>, LlSmem::kTotal)) != cudaSuccess) return e;
     if ((e = ensure_dynamic_smem(lu_trsm_kernel, MmaSmem::kTotal)) != cudaSuccess) return e;
-    if ((e = ensure_dynamic_smem(lu_cpanel_kernel, 32 * kXposeWarpBytes)) != cudaSuccess) return e;
+    if ((e = ensure_dynamic_smem(lu_cpanel_kernel<1>, 32 * kXposeWarpBytes)) != cudaSuccess) return e;
+    if ((e = ensure_dynamic_smem(lu_cpanel_kernel<2>, 16 * kXposeWarpBytes)) != cudaSuccess) return e;
     const long nn = (long)n * n;
     const int panels = n / NB;
     // workspace per matrix: M2, UT (n x n), PWT, T0 (n x 128), W (128 x 128), posmap history; the batch is walked in

@@ -19,10 +19,15 @@ from hls_designs_b200 import _lib  # noqa: E402
 
 if "--old" in sys.argv:
     hd.set_option("lu_tensor", 1)
+for a in sys.argv[1:]:
+    if a.startswith("--opt="):
+        name, val = a[6:].split(":")
+        hd.set_option(name, int(val))
+quick = "--quick" in sys.argv
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 tb = int(args[0]) if args else 1024
 
-for n, batch in ((256, 3), (512, 2), (1024, 2)):
+for n, batch in ((256, 3), (512, 2), (1024, 2)) if not quick else ((256, 2), (1024, 1)):
     rng = np.random.default_rng(n)
     for kind in ("int", "normal"):
         A = rng.integers(1, 101, (batch, n, n)).astype(np.float32) if kind == "int" else rng.standard_normal((batch, n, n)).astype(np.float32)
