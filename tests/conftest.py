@@ -89,3 +89,32 @@ def lu_residual(A, L, U, P):
 def qr_residual(A, Q, R):
     A64 = A.astype(np.float64)
     return np.linalg.norm(A64 - Q.astype(np.float64) @ R.astype(np.float64), axis=(-2, -1)) / np.linalg.norm(A64, axis=(-2, -1))
+
+
+def lu_fp64_following(A, P):
+    """The reference's elimination (lu_v1.1/model4x4/lu.cpp:43-91) in float64 with the pivot sequence P imposed: the
+    yardstick for element-wise errors - how far fp32 round-off alone moves L and U for this operand and these pivots."""
+    n = A.shape[-1]
+    w = A.astype(np.float64).copy()
+    L = np.eye(n)
+    for k in range(n - 1):
+        p = int(P[k])
+        if p != k:
+            w[[k, p], k:] = w[[p, k], k:]
+        w[k + 1:, k] /= w[k, k]
+        L[k + 1:, k] = w[k + 1:, k]
+        w[k + 1:, k + 1:] -= np.outer(w[k + 1:, k], w[k, k + 1:])
+    return L, np.triu(w)
+
+
+def lu_elementwise_ok(A, L, U, P, wl, wu, tol=1e-3, slack=4.0):
+    """Element-wise agreement of a tolerance-exact LU with the csim's (same pivots): within `tol` (max |dL|, max |dU| /
+    max |U|), or - for the few ill-conditioned trailing elements where the csim's own fp32 round-off exceeds `tol` -
+    within `slack` times the csim's own distance from the float64 factors."""
+    el, eu = np.abs(L - wl).max(), np.abs(U - wu).max() / np.abs(wu).max()
+    if el < tol and eu < tol:
+        return True, (el, eu)
+    L64, U64 = lu_fp64_following(A, P)
+    ref_l, ref_u = np.abs(wl - L64).max(), np.abs(wu - U64).max() / np.abs(U64).max()
+    got_l, got_u = np.abs(L - L64).max(), np.abs(U - U64).max() / np.abs(U64).max()
+    return (got_l < max(tol, slack * ref_l) and got_u < max(tol, slack * ref_u)), (el, eu, got_l, ref_l, got_u, ref_u)

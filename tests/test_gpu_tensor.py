@@ -61,7 +61,8 @@ def _lu_check(A, L, U, P, want):
         assert np.abs(L[b]).max() <= 1.0 + 1e-6  # partial pivoting bounds the multipliers
         res = lu_residual(A[b], L[b], U[b], P[b])
         same = np.array_equal(P[b], wp[b])
-        err = max(np.abs(L[b] - wl[b]).max(), np.abs(U[b] - wu[b]).max() / np.abs(wu[b]).max()) if same else None
+        from conftest import lu_elementwise_ok
+        err = lu_elementwise_ok(A[b], L[b], U[b], P[b], wl[b], wu[b]) if same else None
         out.append((res, same, err))
     return out
 
@@ -79,11 +80,11 @@ def test_tensor_lu_vs_oracle(n, batch):
         from conftest import lu_residual
         ref_res = max(lu_residual(A[b], want[0][b], want[1][b], want[2][b]) for b in range(batch))
         checks = _lu_check(A, L, U, P, want)
-        print(f"n={n}:", [(f"{r:.2e}", s, None if e is None else f"{e:.2e}") for r, s, e in checks], f"oracle residual {ref_res:.2e}")
+        print(f"n={n}:", [(f"{r:.2e}", s, None if e is None else tuple(f"{x:.1e}" for x in e[1])) for r, s, e in checks], f"oracle residual {ref_res:.2e}")
         for res, same, err in checks:
             assert res < 5e-5
             if same:
-                assert err < 1e-3
+                assert err[0], err[1]  # 1e-3, or 4x the csim's own distance from the float64 factors where that is larger
         # The csim's pivot sequence is reproduced on most operands, and on the reference's own op256.bin / op512.bin
         # (test_reference_large_operands_tensor_path asserts those exactly).  It is not a guarantee: where two
         # candidates agree to a few ulp, 3xTF32 rounding can order them differently, after which L and U differ
@@ -129,7 +130,9 @@ def test_full_size_tensor_paths_n1024_properties():
         assert lu_residual(Bh[b], Lh[b], Uh[b], Ph[b]) < 5e-5
         if np.array_equal(Ph[b], wp[b]):
             same += 1
-            assert np.abs(Lh[b] - wl[b]).max() < 1e-3 and np.abs(Uh[b] - wu[b]).max() / np.abs(wu[b]).max() < 1e-3
+            from conftest import lu_elementwise_ok
+            ok, detail = lu_elementwise_ok(Bh[b], Lh[b], Uh[b], Ph[b], wl[b], wu[b])
+            assert ok, detail
     print(f"tensor LU 1024: {same} of {len(pick)} pivot sequences equal to the oracle's")
     xl, xu, xp = hd.lu(B[tpick].contiguous(), exact=True)  # blocked exact path: bit-identical L, U, P
     assert np.array_equal(xp.cpu().numpy(), wp)
