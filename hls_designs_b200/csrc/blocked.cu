@@ -852,145 +852,25 @@ cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int us
 }
 
 // =================================================================================================
-// Blocked LU with partial pivoting for large N (N a multiple of 128, N <= 1024), batched.
+// Blocked LU with partial pivoting in the reference's EXACT arithmetic (HLSD_PATH_BLOCKED), 256 <= N <= 1024, N a
+// multiple of 128 - the kernels below and blocked_exact.cu.  (The tensor-core LU lives in lu_crout.cu; it shares
+// blk_diag2_kernel<INV_ONLY> through lu_inverse_l11.)
 //
-// Same elimination as the reference's LU designs (LU/lu_v1.1/model4x4/lu.cpp:23-92: pivot = first
-// row with the largest |a_ik|, rows exchanged in columns >= k only, multipliers l_ik = a_ik / a_kk,
-// a_ij -= l_ik u_kj), reorganised right-looking over 128-column panels so that the rank-128
-// trailing update  A22 -= L21 * U12  runs on the tensor cores (3xTF32, as for Cholesky above):
-//
+// Same elimination as the reference's LU designs (LU/lu_v1.1/model4x4/lu.cpp:23-92: pivot = first row with the largest
+// |a_ik|, rows exchanged in columns >= k only, multipliers l_ik = a_ik / a_kk, a_ij -= l_ik u_kj), right-looking over
+// 128-column panels, every update applied in ascending k so that each element sees the reference's operations in the
+// reference's order:
 //   per panel p (columns o .. o+127), all matrices of the batch at once:
-//     1. lu_panel_kernel   (SIMT) pivoted elimination of the (N-o) x 128 panel, thread = row, in four
-//                          32-column sub-panels held in registers; writes L (unit lower) to the L
-//                          buffer, U11 to the working matrix, the pivots to P
+//     1. lu_panel_kernel<true> (SIMT) pivoted elimination of the (N-o) x 128 panel, thread = row, in four 32-column
+//                          sub-panels held in registers; writes L (unit lower) to the L buffer, U11 to the working
+//                          matrix, the pivots to P
 //     2. lu_swap_kernel    (SIMT) the panel's row exchanges applied to the columns right of the panel
-//     8. lu_unswap_panel_kernel (SIMT) inside a panel rows are exchanged whole (the deferred block updates
-//                          need L in final row order); once L21 has served as operand, the panel's L
-//                          columns go back to the reference's convention (multipliers stay where they
-//                          were computed); exchanges of later panels never touch them
-//     3. blk_diag_kernel<INV_ONLY> (SIMT) W = inv(L11), unit lower triangular
-//     4. lu_gather_kernel  (SIMT) T0 = A12^T  (k contiguous: the tensor core wants K-major operands)
-//     5. gemm_tile_kernel<0> (tcgen05) T1 = T0 * W^T = U12^T
-//     6. lu_scatter_kernel (SIMT) U12 = T1^T back into the working matrix
-//     7. gemm_tile_kernel<1> (tcgen05) A22 -= L21 * T1^T
+//     3. xlu_u12_and_update (blocked_exact.cu) U12 by forward substitution, then the trailing update on SIMT tiles
+//     4. lu_unswap_panel_kernel (SIMT) inside a panel rows are exchanged whole (the deferred block updates need L in
+//                          final row order); once L21 has served as operand, the panel's L columns go back to the
+//                          reference's convention (multipliers stay where they were computed)
 // The working matrix is the U output buffer (a copy of A); what remains in it at the end is U.
-// Not bit-identical to the csim (tensor-core arithmetic; a near-tie between pivot candidates can
-// resolve differently): checked by ||A - P^T L U|| / ||A|| and, where the pivot sequences agree,
-// element-wise.  The exact LU kernels (HLSD_PATH_GLOBAL) stay available at any N.
 // =================================================================================================
-struct TileArgs {
-    const float* A; long lda, strideA;        // A rows of tile row tr: A + b*strideA + (tr*128 + r)*lda + k
-    const float* B; long ldb, strideB;        // B rows of tile col tc: B + b*strideB + (tc*128 + r)*ldb + k
-    const float* Csrc; float* Cdst; long ldc, strideC;  // C tile: + b*strideC + (tr*128 + r)*ldc + tc*128 + c
-    int tiles_col;                            // blockIdx.x -> (tr, tc) = (x / tiles_col, x % tiles_col)
-};
-
-// D = A * B^T over K = 128; SUB ? Cdst = Csrc - D : Cdst = D.  Same pipeline as blk_mma_kernel.
-template <int SUB>
-__global__ void __launch_bounds__(256, MmaSmem::kStages == 1 ? 3 : 2)
-gemm_tile_kernel(TileArgs g) {
-    extern __shared__ unsigned char smem_raw[];
-    // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the address space: LDS/STS, not generic LD/ST)
-    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + MmaSmem::kBar);
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + MmaSmem::kTmemPtr);
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int tr = blockIdx.x / g.tiles_col, tc = blockIdx.x % g.tiles_col;
-    const long b = blockIdx.y;
-    const float* Arows = g.A + b * g.strideA + (long)tr * NB * g.lda;
-    const float* Brows = g.B + b * g.strideB + (long)tc * NB * g.ldb;
-    if (warp == 0) tmem_alloc(tmem_ptr, 128);
-    if (t == 0) {
-        mbar_init(bar, 1);
-        fence_mbar_init();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_d = *tmem_ptr;
-    constexpr int kChunks = NB / MmaSmem::kChunkK;
-    auto piece_off = [&](int it) {
-        const int idx = it * 256 + t, row = idx >> 3, c4 = idx & 7;
-        return row * 128 + ((c4 ^ (row & 7)) << 4);
-    };
-    unsigned char* ra = smem + MmaSmem::kRawA;
-    unsigned char* rb = smem + MmaSmem::kRawB;
-    unsigned char* la = smem + MmaSmem::kLoA;
-    unsigned char* lb = smem + MmaSmem::kLoB;
-    auto issue_loads = [&](int chunk) {
-#pragma unroll
-        for (int it = 0; it < 4; it++) {
-            const int idx = it * 256 + t, row = idx >> 3, c4 = idx & 7;
-            cp_async16(ra + piece_off(it), Arows + row * g.lda + chunk * MmaSmem::kChunkK + c4 * 4);
-            cp_async16(rb + piece_off(it), Brows + row * g.ldb + chunk * MmaSmem::kChunkK + c4 * 4);
-        }
-        cp_async_commit();
-    };
-    issue_loads(0);
-    for (int chunk = 0; chunk < kChunks; chunk++) {
-        cp_async_wait<0>();
-#pragma unroll
-        for (int it = 0; it < 4; it++) {
-            const int off = piece_off(it);
-            *reinterpret_cast<float4*>(la + off) = lo_of(*reinterpret_cast<const float4*>(ra + off));
-            *reinterpret_cast<float4*>(lb + off) = lo_of(*reinterpret_cast<const float4*>(rb + off));
-        }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (t == 0) {
-            const uint64_t dAhi = make_sw128_desc(smem_u32(ra)), dAlo = make_sw128_desc(smem_u32(la));
-            const uint64_t dBhi = make_sw128_desc(smem_u32(rb)), dBlo = make_sw128_desc(smem_u32(lb));
-#pragma unroll
-            for (int kk = 0; kk < MmaSmem::kChunkK / 8; kk++) {
-                const uint64_t adv = (uint64_t)((kk * 32) >> 4);
-                const uint32_t first = (chunk == 0 && kk == 0) ? 0u : 1u;
-                umma_tf32(tmem_d, dAlo + adv, dBhi + adv, kIdescTf32, first);
-                umma_tf32(tmem_d, dAhi + adv, dBlo + adv, kIdescTf32, 1u);
-                umma_tf32(tmem_d, dAhi + adv, dBhi + adv, kIdescTf32, 1u);
-            }
-            umma_commit(bar);
-        }
-        mbar_wait(bar, (uint32_t)(chunk & 1));
-        tc_fence_after();
-        if (chunk + 1 < kChunks) issue_loads(chunk + 1);
-    }
-    {
-        float* stage = reinterpret_cast<float*>(smem);
-        const int drow = (warp & 3) * 32 + lane;
-        const int dcol0 = (warp >> 2) * 64;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            float acc[32];
-            const int col = dcol0 + h * 32;
-            tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col, acc);
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const int c4 = (col >> 2) + q;
-                *reinterpret_cast<float4*>(stage + drow * 128 + ((c4 ^ (drow & 7)) << 2)) =
-                    make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-            }
-        }
-        __syncthreads();
-        const long coff = b * g.strideC + (long)tr * NB * g.ldc + (long)tc * NB;
-#pragma unroll 4
-        for (int rr = 0; rr < 16; rr++) {
-            const int row = warp * 16 + rr;
-            const float4 d = *reinterpret_cast<const float4*>(stage + row * 128 + ((lane ^ (row & 7)) << 2));
-            float4 v = d;
-            if constexpr (SUB) {
-                v = *(reinterpret_cast<const float4*>(g.Csrc + coff + (long)row * g.ldc) + lane);
-                v.x -= d.x, v.y -= d.y, v.z -= d.z, v.w -= d.w;
-            }
-            *(reinterpret_cast<float4*>(g.Cdst + coff + (long)row * g.ldc) + lane) = v;
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_d, 128);
-}
-
 struct PivCand {
     float v;
     int i;
@@ -1281,27 +1161,6 @@ lu_unswap_panel_kernel(float* __restrict__ L, const int* __restrict__ P, int n, 
     }
 }
 
-// T[c][k] = Wk[o + k][o + 128 + c] (gather) or the reverse (scatter); 32 x 32 tiles through shared memory.
-// grid: (ncols / 32, 4, batch), block (32, 8)
-template <int SCATTER>
-__global__ void __launch_bounds__(256)
-lu_transpose_kernel(float* __restrict__ Wk, float* __restrict__ T, int n, int o) {
-    __shared__ float tile[32][33];
-    float* wk = Wk + (long)blockIdx.z * n * n + (long)o * n + o + NB;  // A12: 128 x ncols, ld n
-    float* tt = T + (long)blockIdx.z * n * NB;                          // ncols x 128, ld 128
-    const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    if (!SCATTER) {
-        for (int r = ty; r < 32; r += 8) tile[r][tx] = wk[(long)(k0 + r) * n + c0 + tx];
-        __syncthreads();
-        for (int r = ty; r < 32; r += 8) tt[(long)(c0 + r) * NB + k0 + tx] = tile[tx][r];
-    } else {
-        for (int r = ty; r < 32; r += 8) tile[r][tx] = tt[(long)(c0 + r) * NB + k0 + tx];
-        __syncthreads();
-        for (int r = ty; r < 32; r += 8) wk[(long)(k0 + r) * n + c0 + tx] = tile[tx][r];
-    }
-}
-
 constexpr int kUnswapThreads = 1024;  // the gather / scatter of the touched rows is latency bound: more loads in flight
 
 // W = inv(L11) for the Crout LU (lu_crout.cu): L11 = rows posmap[o .. o+127] of M2, columns o .. o+127 (unit lower)
@@ -1311,111 +1170,6 @@ cudaError_t lu_inverse_l11(const float* M2, const int* posmap, float* W, int n, 
     blk_diag2_kernel<true><<<(unsigned)batch, 256, Diag2::kBytes, st>>>(M2, W, W, n, o, posmap);
     count_launch();
     return cudaGetLastError();
-}
-
-// Round-1/2 right-looking form (one rank-128 tensor update per panel, rows exchanged physically): kept while the Crout
-// form (lu_crout.cu) is being measured against it (HLSD_OPT_LU_TENSOR = 1).
-cudaError_t lu_blocked_rl(const float* A, float* L, float* U, int* P, int n, long batch, cudaStream_t st) {
-    if (n % NB != 0 || n < 2 * NB || n > 1024) return cudaErrorNotSupported;
-    if ((((uintptr_t)A | (uintptr_t)L | (uintptr_t)U) & 15) != 0) return cudaErrorNotSupported;
-    if (batch == 0) return cudaSuccess;
-    if (batch > 65535) return cudaErrorNotSupported;
-    cudaError_t e;
-    const size_t unswap_smem = (size_t)2 * NB * (NB + 1) * sizeof(float) + (size_t)n * sizeof(int);
-    if ((e = ensure_dynamic_smem(lu_unswap_panel_kernel, unswap_smem)) != cudaSuccess) return e;
-    if ((e = ensure_dynamic_smem(blk_diag_kernel<DIAG_INV_ONLY>, kDiagSmem)) != cudaSuccess) return e;
-    if ((e = ensure_dynamic_smem(blk_diag2_kernel<true>, Diag2::kBytes)) != cudaSuccess) return e;
-    const bool old_diag = option(HLSD_OPT_DIAG_KERNEL) == 1;
-    if ((e = ensure_dynamic_smem(gemm_tile_kernel<0>, MmaSmem::kTotal)) != cudaSuccess) return e;
-    if ((e = ensure_dynamic_smem(gemm_tile_kernel<1>, MmaSmem::kTotal)) != cudaSuccess) return e;
-    // one workspace: W = inv(L11) per matrix, T0 = A12^T, T1 = U12^T
-    const size_t w_floats = (size_t)batch * NB * NB, t_floats = (size_t)batch * n * NB;
-    float* ws = nullptr;
-    if ((e = ws_alloc(reinterpret_cast<void**>(&ws), sizeof(float) * (w_floats + 2 * t_floats), st)) != cudaSuccess) return e;
-    float *Winv = ws, *T0 = ws + w_floats, *T1 = T0 + t_floats;
-    const unsigned nb = (unsigned)batch;
-    const long nn = (long)n * n;
-    {
-        ProfScope ps(HLSD_PROF_OTHER, st);
-        e = cudaMemcpyAsync(U, A, sizeof(float) * (size_t)batch * nn, cudaMemcpyDeviceToDevice, st);
-    }
-    if (e != cudaSuccess) {
-        ws_free(ws, st);
-        return e;
-    }
-    const int panels = n / NB;
-    {
-        ProfScope ps(HLSD_PROF_OTHER, st);
-        blk_zero_upper_kernel<<<dim3(panels * (panels - 1) / 2, nb), 256, 0, st>>>(L, n);
-        count_launch();
-    }
-    for (int p = 0; p < panels; p++) {
-        const int o = p * NB;
-        const int mt = panels - p - 1, ncols = mt * NB;
-        // thread = row of the panel: later panels are shorter and run with fewer (cheaper to synchronise) threads
-        {
-            ProfScope ps(HLSD_PROF_PANEL, st);
-            lu_panel_kernel<false><<<nb, std::max(256, n - o), 0, st>>>(U, L, P, n, o);
-            count_launch();
-        }
-        if (mt == 0) {  // last panel: nothing to update, only its L columns go back to the reference's convention
-            {
-                ProfScope ps(HLSD_PROF_PERMUTE, st);
-                lu_unswap_panel_kernel<<<nb, kUnswapThreads, unswap_smem, st>>>(L, P, n, o);
-                count_launch();
-            }
-            break;
-        }
-        {
-            ProfScope ps(HLSD_PROF_PERMUTE, st);
-            lu_swap_kernel<<<dim3((ncols + 127) / 128, nb), 128, n * sizeof(int), st>>>(U, P, n, o);
-            count_launch();
-        }
-        {
-            ProfScope ps(HLSD_PROF_DIAG, st);
-            if (old_diag) blk_diag_kernel<DIAG_INV_ONLY><<<nb, 512, kDiagSmem, st>>>(L, L, Winv, n, o);  // W = inv(L11), L11 unit lower
-            else blk_diag2_kernel<true><<<nb, 256, Diag2::kBytes, st>>>(L, L, Winv, n, o);
-            count_launch();
-        }
-        {
-            ProfScope ps(HLSD_PROF_PERMUTE, st);
-            lu_transpose_kernel<0><<<dim3(ncols / 32, 4, nb), dim3(32, 8), 0, st>>>(U, T0, n, o);
-            count_launch();
-        }
-        TileArgs g{};
-        g.A = T0, g.lda = NB, g.strideA = (long)n * NB;
-        g.B = Winv, g.ldb = NB, g.strideB = (long)NB * NB;
-        g.Csrc = T1, g.Cdst = T1, g.ldc = NB, g.strideC = (long)n * NB;
-        g.tiles_col = 1;
-        {
-            ProfScope ps(HLSD_PROF_TRSM, st);
-            gemm_tile_kernel<0><<<dim3(mt, nb), 256, MmaSmem::kTotal, st>>>(g);
-            count_launch();
-        }
-        {
-            ProfScope ps(HLSD_PROF_PERMUTE, st);
-            lu_transpose_kernel<1><<<dim3(ncols / 32, 4, nb), dim3(32, 8), 0, st>>>(U, T1, n, o);
-            count_launch();
-        }
-        TileArgs h{};
-        h.A = L + (long)(o + NB) * n + o, h.lda = n, h.strideA = nn;
-        h.B = T1, h.ldb = NB, h.strideB = (long)n * NB;
-        h.Csrc = U + (long)(o + NB) * n + (o + NB), h.Cdst = U + (long)(o + NB) * n + (o + NB), h.ldc = n, h.strideC = nn;
-        h.tiles_col = mt;
-        {
-            ProfScope ps(HLSD_PROF_UPDATE, st);
-            gemm_tile_kernel<1><<<dim3(mt * mt, nb), 256, MmaSmem::kTotal, st>>>(h);
-            count_launch();
-        }
-        {
-            ProfScope ps(HLSD_PROF_PERMUTE, st);
-            lu_unswap_panel_kernel<<<nb, kUnswapThreads, unswap_smem, st>>>(L, P, n, o);  // L21 has served as operand
-            count_launch();
-        }
-    }
-    e = cudaGetLastError();
-    ws_free(ws, st);
-    return e;
 }
 
 // Blocked LU in the reference's exact arithmetic (HLSD_FLAG_EXACT / HLSD_PATH_BLOCKED, 256 <= n <= 1024): the structure

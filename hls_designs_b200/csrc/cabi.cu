@@ -205,7 +205,7 @@ static int lu_dev(const float* A, float* L, float* U, int32_t* P, int n, int64_t
         for (int64_t b0 = 0; b0 < batch && e == cudaSuccess; b0 += kSlice) {
             const int64_t cnt = batch - b0 < kSlice ? batch - b0 : kSlice;
             e = path == HLSD_PATH_TENSOR
-                    ? (option(HLSD_OPT_LU_TENSOR) == 1 ? lu_blocked_rl : lu_blocked)(A + b0 * n * n, L + b0 * n * n, U + b0 * n * n, P + b0 * n, n, (long)cnt, st)
+                    ? lu_blocked(A + b0 * n * n, L + b0 * n * n, U + b0 * n * n, P + b0 * n, n, (long)cnt, st)
                     : lu_blocked_exact(A + b0 * n * n, L + b0 * n * n, U + b0 * n * n, P + b0 * n, n, (long)cnt, st);
         }
         if (e == cudaErrorNotSupported) return fail(HLSD_ERR_UNSUPPORTED, "the blocked LU paths need n % 128 == 0, 256 <= n <= 1024 and 16-byte aligned buffers");

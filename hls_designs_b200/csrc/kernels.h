@@ -55,9 +55,8 @@ cudaError_t cholesky_tile_exact(const float* S, float* L, int m, int n, int o, l
 cudaError_t cholesky128_exact(const float* A, float* L, long batch, int fused, cudaStream_t st);
 
 // Blocked LU with partial pivoting on the tensor cores (n % 128 == 0, 256 <= n <= 1024): Crout order, rows never
-// moved (lu_crout.cu).  lu_blocked_rl: the right-looking form of rounds 1-2 (HLSD_OPT_LU_TENSOR = 1, A/B only).
+// moved (lu_crout.cu).
 cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long batch, cudaStream_t st);
-cudaError_t lu_blocked_rl(const float* A, float* L, float* U, int* P, int n, long batch, cudaStream_t st);
 
 // The same factorisation in the reference's exact arithmetic and per-element order (bit-identical L, U, P).
 cudaError_t lu_blocked_exact(const float* A, float* L, float* U, int* P, int n, long batch, cudaStream_t st);

@@ -150,10 +150,8 @@ const char* hlsd_version(void);
 #define HLSD_OPT_CHOL_TILE 6    /* exact Cholesky 64 / 128 (right-looking designs): 0 = shared-memory tile kernel blocked by
                                    32 columns (default), 1 = the register kernels of round 1, 2 = tile kernel with 64
                                    instead of 128 threads per 64x64 matrix                                             */
-#define HLSD_OPT_LU_TENSOR 7    /* tensor LU (256 <= n <= 1024): 0 = Crout order, rows never moved (default), 1 = the
-                                   right-looking form of rounds 1-2 (rank-128 update per panel, rows exchanged in memory) */
-#define HLSD_OPT_LU_PANEL_ROWS 8 /* tensor LU panel kernel: 0 = two rows per thread (default), 1 = one row per thread         */
-#define HLSD_OPT_COUNT 9
+#define HLSD_OPT_LU_PANEL_ROWS 7 /* tensor LU panel kernel: 0 = two rows per thread (default), 1 = one row per thread         */
+#define HLSD_OPT_COUNT 8
 int hlsd_set_option(int option, int value);
 
 /* ---- per-kernel-class timing of the blocked paths (diagnostic; used by bench.py for the roofline of the dominant

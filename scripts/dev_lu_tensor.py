@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Tensor LU (lu_crout.cu) on the GPU: correctness diagnosis against the oracle at 256/512/1024 and per-kernel-class
-times at N = 1024.  Usage: python scripts/dev_lu_tensor.py [batch_for_timing] [--old]"""
+times at N = 1024.  Usage: python scripts/dev_lu_tensor.py [batch_for_timing] [--quick] [--opt=name:value]"""
 import ctypes
 import os
 import sys
@@ -17,8 +17,6 @@ import restate  # noqa: E402
 from conftest import lu_residual  # noqa: E402
 from hls_designs_b200 import _lib  # noqa: E402
 
-if "--old" in sys.argv:
-    hd.set_option("lu_tensor", 1)
 for a in sys.argv[1:]:
     if a.startswith("--opt="):
         name, val = a[6:].split(":")
