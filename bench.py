@@ -107,9 +107,12 @@ def flops(kind, rows, cols):
 
 def update_flops_executed(kind, n):
     """Flops the tcgen05 trailing-update kernel executes per matrix (3xTF32: three MMAs per product):
-    Cholesky left-looking: tile (r, q) takes q tile products, r >= q; LU right-looking: mt^2 tiles per panel."""
+    Cholesky left-looking: tile (r, q) takes q tile products, r >= q; LU in Crout order (lu_ll_kernel): panel q's
+    column form (p - q row tiles) and row form (p - 1 - q column tiles) each take q tile products per tile."""
     p = n // 128
-    tiles = sum((p - q) * q for q in range(p)) if kind == "chol" else sum(mt * mt for mt in range(1, p))
+    tiles = sum((p - q) * q for q in range(p))
+    if kind == "lu":
+        tiles += sum((p - 1 - q) * q for q in range(p))
     return 3.0 * tiles * 2.0 * 128 ** 3
 
 
@@ -375,7 +378,7 @@ class Runner:
             upd_ms = by_class.get("update", float("nan"))
             upd_tf = update_flops_executed(kind, rows) * batch / (upd_ms * 1e-3) / 1e12
             res["roofline"] = {"bound": "tensor", "achieved": upd_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": upd_tf / peak_tf,
-                               "traffic": None, "kernel": "blk_ll2_kernel" if kind == "chol" else "gemm_tile_kernel<1>",
+                               "traffic": None, "kernel": "blk_ll2_kernel" if kind == "chol" else "lu_ll_kernel<LL_COL|LL_ROW>",
                                "kernel_ms_per_step": upd_ms, "kernel_share_of_step": share.get("update"),
                                "ms_per_step_by_kernel_class": by_class, "share_by_kernel_class": share,
                                "whole_step": {"useful_tflops": gflops / 1e3, "frac_of_tf32_peak": gflops / 1e3 / peak_tf,

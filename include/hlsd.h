@@ -160,11 +160,11 @@ int hlsd_set_option(int option, int value);
  * ms[0..n-1] (classes >= n are dropped) and the launch counts to launches[0..n-1] (may be NULL).  Process-wide; not
  * meant to stay on in production (two events per launch). */
 #define HLSD_PROF_OTHER 0    /* zero fill, copies of the working matrix                                      */
-#define HLSD_PROF_UPDATE 1   /* tcgen05 trailing update: blk_ll2_kernel (Cholesky), gemm_tile_kernel<1> (LU)  */
+#define HLSD_PROF_UPDATE 1   /* tcgen05 long-K updates: blk_ll2_kernel (Cholesky), lu_ll_kernel (LU)          */
 #define HLSD_PROF_DIAG 2     /* SIMT diagonal block: Cholesky + inverse / inverse of the unit-lower LU block   */
-#define HLSD_PROF_TRSM 3     /* tcgen05 panel solve: blk_mma_kernel (Cholesky), gemm_tile_kernel<0> (LU)       */
+#define HLSD_PROF_TRSM 3     /* tcgen05 panel solve: blk_mma_kernel (Cholesky), lu_trsm_kernel (LU)            */
 #define HLSD_PROF_PANEL 4    /* SIMT pivoted panel factorisation of the blocked LU                            */
-#define HLSD_PROF_PERMUTE 5  /* row exchanges, un-exchanges and transposes of the blocked LU                   */
+#define HLSD_PROF_PERMUTE 5  /* tensor LU: assembly of L from the multiplier store; exact blocked LU: exchanges */
 #define HLSD_PROF_EXACT 6    /* the exact (register / shared-memory / global) kernels                          */
 #define HLSD_PROF_CLASSES 7
 int hlsd_profile_begin(void);
