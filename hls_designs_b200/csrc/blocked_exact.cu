@@ -390,11 +390,14 @@ xchol_update_kernel(const float* __restrict__ Csrc, float* __restrict__ Cdst, co
     for (int k = 0; k < XB; k++) {  // ascending k: the reference's order for every element
         const float4 av = *reinterpret_cast<const float4*>(As + k * LDK + i0);
         const float4 bv = *reinterpret_cast<const float4*>(Bt + k * LDK + j0);
-        const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+        // two columns per instruction (FMUL2 / FFMA2, common.cuh): (c[a][0], c[a][1]) -= a * (b0, b1), each lane rounded
+        // twice like the scalar pair
+        const float a4[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int b = 0; b < 4; b++) c[a][b] = xmsub(c[a][b], a4[a], b4[b]);
+        for (int a = 0; a < 4; a++) {
+            msub_pair<false>(c[a][0], c[a][1], a4[a], bv.x, bv.y);
+            msub_pair<false>(c[a][2], c[a][3], a4[a], bv.z, bv.w);
+        }
     }
     float* cdst = Cdst + mat + (long)(ri0 + i0) * n + rj0 + j0;
 #pragma unroll

@@ -291,12 +291,33 @@ chol_rows_kernel(const float* __restrict__ A, float* __restrict__ L, long batch)
                     if (t > tk || r > rk) a[t][k] = own[t];
             }
             // all-gather column k (rows k+1 .. N-1) and update
+            if constexpr (N >= 32) {
+                // two columns per instruction (FMUL2 / FFMA2, common.cuh): columns (i, i+1), i even, have the same row
+                // range t >= i/R (R is even); an odd first column goes alone
+                constexpr int i0 = (k + 1) | 1;  // first odd column >= k+1 ... pairs start at the even column after it
+                if constexpr ((k + 1) % 2 == 1 && k + 1 < N) {
+                    constexpr int i = k + 1;
+                    const float lik = __shfl_sync(0xffffffffu, own[i / R], gbase + (i % R));
+#pragma unroll
+                    for (int t = i / R; t < T; t++) a[t][i] = msub<FUSED>(a[t][i], a[t][k], lik);
+                }
+                constexpr int ie = ((k + 1) % 2 == 1) ? k + 2 : k + 1;  // even
+                (void)i0;
+#pragma unroll
+                for (int i = ie; i + 1 < N; i += 2) {
+                    const float l0 = __shfl_sync(0xffffffffu, own[i / R], gbase + (i % R));
+                    const float l1 = __shfl_sync(0xffffffffu, own[(i + 1) / R], gbase + ((i + 1) % R));
+#pragma unroll
+                    for (int t = i / R; t < T; t++) msub_pair<FUSED>(a[t][i], a[t][i + 1], a[t][k], l0, l1);
+                }
+            } else {
 #pragma unroll
             for (int i = k + 1; i < N; i++) {
                 const float lik = __shfl_sync(0xffffffffu, own[i / R], gbase + (i % R));
                 // rows j = t*R + r >= i  <=>  t >= i/R (the t == i/R case is scratch when r < i % R)
 #pragma unroll
                 for (int t = i / R; t < T; t++) a[t][i] = msub<FUSED>(a[t][i], a[t][k], lik);
+            }
             }
             if constexpr (VARIANT == 1) {
 #pragma unroll

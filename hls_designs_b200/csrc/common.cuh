@@ -75,6 +75,44 @@ __device__ __forceinline__ float msub(float a, float b, float c) {
     else return xmsub(a, b, c);
 }
 
+// ----------------------------------------------------------------------------------------------
+// Packed fp32 pairs (sm_100a FMUL2 / FFMA2): one instruction works on two floats held in an aligned register pair,
+// each lane rounded like the scalar instruction.  The exact kernels are bound by instruction issue and fetch, not by
+// the FP32 pipe, so the separately rounded a - b*c costs half the instructions this way:  m = b*c (FMUL2, rounded),
+// then a - m as fma(m, -1, a): the product m * -1 is exact, so the single rounding of the sum is the rounding of the
+// subtraction.  (mul.f32x2 followed directly by sub.f32x2 is NOT safe: ptxas contracts that pair into FFMA2 even
+// with --fmad=false; it cannot contract a product that feeds the multiplicand of an fma.)
+// ----------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 xmul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// (a.lo - b.lo*c.lo, a.hi - b.hi*c.hi), two roundings per lane; FUSED: one (nb = -b must be passed as well)
+template <bool FUSED>
+__device__ __forceinline__ f32x2 msub2(f32x2 a, f32x2 b, f32x2 nb, f32x2 c) {
+    if constexpr (FUSED) return fma2(nb, c, a);
+    else return fma2(xmul2(b, c), 0xBF800000BF800000ULL, a);
+}
+// the same on four scalars: (x0, x1) -= b * (c0, c1)
+template <bool FUSED>
+__device__ __forceinline__ void msub_pair(float& x0, float& x1, float b, float c0, float c1) {
+    const f32x2 r = msub2<FUSED>(pack2(x0, x1), pack2(b, b), pack2(-b, -b), pack2(c0, c1));
+    unpack2(r, x0, x1);
+}
+
 // qrf_mm of the reference (QR/qr_v2.1/model4x4/qr.cpp:52-60): a' = op2*s + op1*c ; b' = op2*c - op1*s
 __device__ __forceinline__ void givens_apply(float c, float s, float& op1, float& op2) {
     float a = xadd(xmul(op2, s), xmul(op1, c));
