@@ -668,136 +668,10 @@ qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Wavefront with R AND Q in registers (qr_v2.1 arithmetic, square N = 64, 128): one CTA of 2 N threads per matrix.
-// Thread x < N keeps COLUMN x of R in N registers, thread N + j keeps ROW j of Q.  Both see a rotation as the same
-// thing - the pair of registers (2p + par - 1, 2p + par) of slot p = p0 + c combined with (c, s) - so one unrolled slot
-// loop (constant register indices, as in qr_qreg_kernel) serves both roles; what differs is the range of active slots:
-// a Q row takes every rotation c_lo..c_hi of the step, column x of R only those with c < x.
-// Angle generation needs no pass over shared memory and no second barrier: column x generates its own rotation
-// (c = x) from two values it already holds -
-//   high input: the magnitude its own rotation of the previous step left one row further down (`carry`; the first
-//               time: its bottom element),
-//   low input:  the high output of rotation c = x - 1 applied to this column in the previous step (`nextlo`, captured
-//               in the slot loop when p == p0 + x - 1; column 0, which no rotation ever modifies, reads A itself) -
-// publishes (c, s) in a buffer double-buffered by the parity of the step, ONE barrier, then everybody applies the
-// step's rotations.  The element a rotation zeroes is final (no later rotation touches it) and goes straight into the
-// shared-memory image of R that is written out at the end; the rest of the column follows from the registers.
-// Same operations on every element in the same order as qr_factor / the sequential loop: bit-identical.
-// ------------------------------------------------------------------------------------------------
-template <int N, bool FUSED>
-__global__ void __launch_bounds__(2 * N, N == 64 ? 4 : 1)
-qr_rreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restrict__ R, long batch) {
-    extern __shared__ __align__(16) float smem_f[];
-    constexpr int ldr = N + 1;
-    float* rout = smem_f;                                              // N x ldr: image of R
-    float* col0 = rout + N * ldr;                                      // column 0 of A
-    float2* cs2 = reinterpret_cast<float2*>(col0 + N + (N & 1)) + 8;   // [2][N + 16]: (c, s) of rotation c, slack around
-    constexpr int kCsLd = N + 16;
-    const int t = threadIdx.x;
-    const bool r_side = t < N;
-    const int x = r_side ? t : t - N;  // column of R / row of Q
-    const int warp_x0 = x & ~31;       // first column (row) of this warp
-    for (long b = blockIdx.x; b < batch; b += gridDim.x) {
-        const float* a = A + b * (long)(N * N);
-        float v[N];
-        if (r_side) {
-#pragma unroll
-            for (int i = 0; i < N; i++) v[i] = a[i * N + x];
-            col0[x] = a[x * N];
-        } else {
-#pragma unroll
-            for (int i = 0; i < N; i++) v[i] = (i == x) ? 1.0f : 0.0f;
-        }
-        float carry = v[N - 1], nextlo = 0.0f;
-        __syncthreads();
-        constexpr int last_t = (N - 1) + 2 * (N - 2);  // the last step with a rotation: (i, c) = (N-1, N-2)
-        for (int step = 0; step <= last_t; step++) {
-            const int c_lo = max(0, step - N + 2);
-            const int c_hi = min(N - 2, step / 2);
-            const int bb = N - 1 - step;  // hi row of rotation c: bb + 2 c
-            const int p0 = bb >> 1;       // floor(bb / 2) (bb may be negative): slot of rotation c is p0 + c
-            float2* csb = cs2 + (step & 1) * kCsLd;
-            if (r_side && x >= c_lo && x <= c_hi) {
-                const int hi_row = bb + 2 * x;
-                float hi = (step == 2 * x) ? v[N - 1] : carry;
-                float lo = (x == 0) ? col0[hi_row - 1] : nextlo;
-                float cc, ss;
-                givens_make_fast<FUSED>(lo, hi, cc, ss);
-                csb[x] = make_float2(cc, ss);
-                carry = lo;
-                rout[hi_row * ldr + x] = hi;  // final: the zero (or the untouched value of a skipped rotation)
-            }
-            __syncthreads();
-            {
-                // Active slots: plo .. phi for EVERY thread.  Column x of R needs only the rotations c < x, but the others
-                // touch rows at or below its own pair, whose registers are dead (their final values are in `rout`, the
-                // live magnitude in `carry`): applying them costs nothing extra and keeps the warp's lanes in step.
-                // The one per-lane item is the capture of `nextlo` at slot cap = p0 + x - 1; only the groups that can
-                // hold a capture slot of this warp carry the two extra instructions.
-                const int plo = p0 + c_lo, phi = p0 + c_hi;
-                const int cap = r_side ? p0 + x - 1 : -0x40000000;
-                const int zlo = r_side ? p0 + warp_x0 - 1 : 0x40000000, zhi = zlo + 31;  // capture zone of this warp
-                const float2* csp = csb - p0;  // slot p reads csp[p]
-                auto run = [&](auto parc) {
-                    constexpr int PAR = decltype(parc)::value;
-                    static_for<0, N / 16>([&](auto gc) {
-                        constexpr int g = decltype(gc)::value;
-                        auto full = [&](auto capc) {
-                            constexpr bool CAPTURE = decltype(capc)::value;
-                            static_for<0, 8>([&](auto ec) {
-                                constexpr int p = 8 * g + decltype(ec)::value;
-                                constexpr int lo = 2 * p + PAR - 1, hi = 2 * p + PAR;
-                                if constexpr (lo >= 0 && hi < N) {
-                                    const float2 w = csp[p];
-                                    givens_apply_t<FUSED>(w.x, w.y, v[lo], v[hi]);
-                                    if constexpr (CAPTURE) nextlo = (p == cap) ? v[hi] : nextlo;
-                                }
-                            });
-                        };
-                        if (8 * g >= plo && 8 * g + 7 <= phi) {
-                            // all eight slots active: straight-line code, the eight loads go out together
-                            if (8 * g + 7 >= zlo && 8 * g <= zhi) full(std::true_type{});
-                            else full(std::false_type{});
-                        } else if (8 * g + 7 >= plo && 8 * g <= phi) {
-                            // partially active group: unconditional loads (slack entries around the buffer), results selected
-                            static_for<0, 8>([&](auto ec) {
-                                constexpr int p = 8 * g + decltype(ec)::value;
-                                constexpr int lo = 2 * p + PAR - 1, hi = 2 * p + PAR;
-                                if constexpr (lo >= 0 && hi < N) {
-                                    const bool on = p >= plo && p <= phi;
-                                    const float2 w = csp[p];
-                                    float x0 = v[lo], x1 = v[hi];
-                                    givens_apply_t<FUSED>(w.x, w.y, x0, x1);
-                                    v[lo] = on ? x0 : v[lo];
-                                    v[hi] = on ? x1 : v[hi];
-                                    nextlo = (on && p == cap) ? x1 : nextlo;
-                                }
-                            });
-                        }
-                    });
-                };
-                if (bb & 1) run(std::integral_constant<int, 1>{});
-                else run(std::integral_constant<int, 0>{});
-            }
-        }
-        // R: rows above the diagonal from the column registers, the diagonal = what the last own rotation left
-        if (r_side) {
-#pragma unroll
-            for (int i = 0; i < N; i++)
-                if (i < x) rout[i * ldr + x] = v[i];
-            rout[x * ldr + x] = (x == N - 1) ? v[N - 1] : carry;
-        } else {
-            float4* q4 = reinterpret_cast<float4*>(Q + b * (long)(N * N) + (long)x * N);
-#pragma unroll
-            for (int i = 0; i < N / 4; i++) q4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-        __syncthreads();
-        float* ro = R + b * (long)(N * N);
-        for (int e = t; e < N * N; e += 2 * N) ro[e] = rout[(e / N) * ldr + (e % N)];
-        __syncthreads();
-    }
-}
+// (Round 2 experiment, removed: the same wavefront with the COLUMNS of R in registers as well - thread x generates its own
+// rotation from a carried magnitude and a captured neighbour value, one barrier per step, 2 N threads and 254 registers
+// per matrix.  Bit-identical, but 344-383 k fact/s at 128 x 128 against 683 k for the kernel above: one matrix per SM
+// leaves 8 warps to hide the instruction fetch of the unrolled slot code (`no_instruction` 2.3 warps per issue).)
 
 template <int VARIANT>
 __global__ void __launch_bounds__(1024)
@@ -887,20 +761,6 @@ static cudaError_t launch_qr_qreg(const float* A, float* Q, float* R, long batch
     return cudaGetLastError();
 }
 
-template <int N, bool FUSED>
-static cudaError_t launch_qr_rreg(const float* A, float* Q, float* R, long batch, cudaStream_t st) {
-    const size_t smem = ((size_t)N * (N + 1) + N + (N & 1) + 2 * (8 + 2 * (N + 16))) * 4;
-    auto kern = qr_rreg_kernel<N, FUSED>;
-    cudaError_t e = ensure_dynamic_smem(kern, smem);
-    if (e != cudaSuccess) return e;
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 2 * N, smem);
-    long grid = std::min<long>(batch, (long)sm_count() * std::max(1, per_sm));
-    kern<<<(unsigned)grid, 2 * N, smem, st>>>(A, Q, R, batch);
-    count_launch();
-    return cudaGetLastError();
-}
-
 static size_t qr_smem_per_matrix(int rows, int cols) {
     return ((size_t)rows * (cols | 1) + (size_t)rows * (rows | 1) + 2 * (rows / 2 + 2)) * 4;
 }
@@ -946,8 +806,6 @@ static cudaError_t qr_dispatch(const float* A, float* Q, float* R, int rows, int
     if (VARIANT == 0 && aligned && rows == cols && path == HLSD_PATH_AUTO) {
         // measured (round 2): one set of threads for R and Q (UNI) 6.22 M / 683 k fact/s at 64 / 128, separate R and Q
         // threads 5.20 M / 541 k
-        if (rows == 128 && option(HLSD_OPT_QR_THREADS) == 0) return launch_qr_rreg<128, FUSED>(A, Q, R, batch, st);
-        if (rows == 64 && option(HLSD_OPT_QR_THREADS) == 3) return launch_qr_rreg<64, FUSED>(A, Q, R, batch, st);
         if (rows == 64 && option(HLSD_OPT_QR_THREADS) != 1) return launch_qr_qreg<64, 64, FUSED, true>(A, Q, R, batch, st);
         if (rows == 128 && option(HLSD_OPT_QR_THREADS) != 1) return launch_qr_qreg<128, 128, FUSED, true>(A, Q, R, batch, st);
         if (rows == 64) return launch_qr_qreg<64, 64, FUSED>(A, Q, R, batch, st);  // (128 R threads, 3 CTAs per SM: 4.0 M vs 5.2 M fact/s)
