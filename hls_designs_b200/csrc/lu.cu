@@ -413,12 +413,17 @@ lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
             constexpr int k = decltype(kc)::value;
             PivotCand c{-2.0f, 0x7fffffff};
             if constexpr (PIVOT && k < N - 1) {
-                if (pos >= k) c = PivotCand{pivot_key(a[k], pos == k), pos};
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    PivotCand o{__shfl_xor_sync(0xffffffffu, c.v, off), __shfl_xor_sync(0xffffffffu, c.i, off)};
-                    c = pivot_better(c, o);
+                // arg-max over the warp with two REDUX instead of a five-level butterfly: the key (-2 = no candidate,
+                // -1 = NaN off the diagonal, else |a| >= 0) is mapped monotonically to an unsigned integer and maximised,
+                // then the smallest position among the lanes that hold the maximum is taken (the reference's tie rule)
+                unsigned uk = 0u;
+                if (pos >= k) {
+                    const float v = pivot_key(a[k], pos == k);
+                    uk = v < 0.0f ? 1u : __float_as_uint(v) + 2u;
                 }
+                const unsigned wmax = __reduce_max_sync(0xffffffffu, uk);
+                const unsigned wpos = __reduce_min_sync(0xffffffffu, (uk == wmax && wmax != 0u) ? (unsigned)pos : 0x7fffffffu);
+                c = PivotCand{wmax >= 2u ? __uint_as_float(wmax - 2u) : (wmax == 1u ? -1.0f : -2.0f), (int)wpos};
             }
             return c;
         };
@@ -469,21 +474,19 @@ lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
                 const float lm = xdiv(act ? a[k] : piv, make_divisor(piv));
                 if (act) sA[pos * LD + k] = lm;
                 constexpr int q1 = (k + 1) / 4;  // the quad of column k+1 first: the next search only needs that column
+                // two columns per instruction (FMUL2 / FFMA2, common.cuh).  Columns <= k of this row are dead data by now
+                // (the multiplier has been taken from a[k]), so the pairs that straddle k are updated whole
                 {
                     const float4 u = ur4[q1];
-                    if (4 * q1 > k) a[4 * q1] = msub<FUSED>(a[4 * q1], lm, u.x);
-                    if (4 * q1 + 1 > k) a[4 * q1 + 1] = msub<FUSED>(a[4 * q1 + 1], lm, u.y);
-                    if (4 * q1 + 2 > k) a[4 * q1 + 2] = msub<FUSED>(a[4 * q1 + 2], lm, u.z);
-                    a[4 * q1 + 3] = msub<FUSED>(a[4 * q1 + 3], lm, u.w);
+                    if (4 * q1 + 1 > k) msub_pair<FUSED>(a[4 * q1], a[4 * q1 + 1], lm, u.x, u.y);
+                    msub_pair<FUSED>(a[4 * q1 + 2], a[4 * q1 + 3], lm, u.z, u.w);
                 }
                 cand = search(std::integral_constant<int, k + 1>{});
 #pragma unroll
                 for (int q = q1 + 1; q < N / 4; q++) {
                     const float4 u = ur4[q];
-                    a[4 * q] = msub<FUSED>(a[4 * q], lm, u.x);
-                    a[4 * q + 1] = msub<FUSED>(a[4 * q + 1], lm, u.y);
-                    a[4 * q + 2] = msub<FUSED>(a[4 * q + 2], lm, u.z);
-                    a[4 * q + 3] = msub<FUSED>(a[4 * q + 3], lm, u.w);
+                    msub_pair<FUSED>(a[4 * q], a[4 * q + 1], lm, u.x, u.y);
+                    msub_pair<FUSED>(a[4 * q + 2], a[4 * q + 3], lm, u.z, u.w);
                 }
             }
         });
