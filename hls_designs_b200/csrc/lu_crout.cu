@@ -386,22 +386,22 @@ struct PCand {
     unsigned key;
     int pos;
 };
-constexpr int kXposeWarpBytes = 32 * 36 * 4;  // dynamic shared memory of lu_cpanel_kernel per warp
+constexpr int kXposeWarpBytes = 32 * 36 * 4;  // dynamic shared memory of lu_cpanel_kernel per warp (sub-panel width 32)
 
 // RPT = rows per thread (thread t holds the rows at positions o + t and o + t + blockDim.x): the per-column work that
 // does not depend on the row count - key reduction, publication, the barrier, the winner test - is paid once per
 // thread, so two rows per thread nearly halve the instructions of the column loop, and the U rows read from shared
 // memory in the rank-32 update serve eight instead of four multiply-adds.
-template <int RPT>
-__global__ void __launch_bounds__(1024 / RPT, 1)
+template <int RPT, int SW>
+__global__ void __launch_bounds__(1024 / RPT, SW == 16 ? 2 : 1)
 lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restrict__ U, int* __restrict__ P,
                  const int* __restrict__ pm_in, int* __restrict__ pm_out, int n, int o) {
-    __shared__ __align__(16) float slot[2][32][32];  // speculative pivot rows, one per warp
+    __shared__ __align__(16) float slot[2][32][SW];  // speculative pivot rows, one per warp
     __shared__ PCand cand[2][32];
-    __shared__ __align__(16) float prow[32][36];     // pivot rows of the sub-panel: multipliers | U11
-    __shared__ int tw[32];                           // row (index into PWT) that won step kk
-    __shared__ __align__(16) float ublk[32][100];    // the sub-panel's U rows in the remaining panel columns (<= 96)
-    extern __shared__ __align__(16) float xpose[];   // [warps][32][36]: per-warp transposition stage of the M2 stores
+    __shared__ __align__(16) float prow[SW][SW + 4];     // pivot rows of the sub-panel: multipliers | U11
+    __shared__ int tw[SW];                           // row (index into PWT) that won step kk
+    __shared__ __align__(16) float ublk[SW][NB - SW + 4];  // the sub-panel's U rows in the remaining panel columns
+    extern __shared__ __align__(16) float xpose[];   // [warps][32][SW + 4]: per-warp transposition stage of the M2 stores
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int T = blockDim.x, nwarps = T >> 5;
     const int R = n - o;
@@ -415,14 +415,14 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
         mypos[i] = ri < R ? o + ri : -1;
     }
     constexpr unsigned kFull = 0xffffffffu;
-    for (int sp = 0; sp < 4; sp++) {
-        const int cs = 32 * sp;
-        float a[RPT][32];
+    for (int sp = 0; sp < NB / SW; sp++) {
+        const int cs = SW * sp;
+        float a[RPT][SW];
 #pragma unroll
         for (int i = 0; i < RPT; i++)
 #pragma unroll
-            for (int j = 0; j < 32; j++) a[i][j] = t + i * T < R ? pwb[(long)(cs + j) * n + t + i * T] : 0.0f;
-        static_for<0, 32>([&](auto kkc) {
+            for (int j = 0; j < SW; j++) a[i][j] = t + i * T < R ? pwb[(long)(cs + j) * n + t + i * T] : 0.0f;
+        static_for<0, SW>([&](auto kkc) {
             constexpr int kk = decltype(kkc)::value;
             constexpr int par = kk & 1;
             const int k = o + cs + kk;
@@ -445,11 +445,11 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
                 float4* dst = reinterpret_cast<float4*>(slot[par][warp]);
                 if (RPT == 2 && mypos[RPT - 1] == (int)wpos) {
 #pragma unroll
-                    for (int q = kk / 4; q < 8; q++)
+                    for (int q = kk / 4; q < SW / 4; q++)
                         dst[q] = make_float4(a[RPT - 1][4 * q], a[RPT - 1][4 * q + 1], a[RPT - 1][4 * q + 2], a[RPT - 1][4 * q + 3]);
                 } else {
 #pragma unroll
-                    for (int q = kk / 4; q < 8; q++) dst[q] = make_float4(a[0][4 * q], a[0][4 * q + 1], a[0][4 * q + 2], a[0][4 * q + 3]);
+                    for (int q = kk / 4; q < SW / 4; q++) dst[q] = make_float4(a[0][4 * q], a[0][4 * q + 1], a[0][4 * q + 2], a[0][4 * q + 3]);
                 }
             }
             __syncthreads();
@@ -467,7 +467,7 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
                     tw[kk] = t + i * T;
                     float4* dst = reinterpret_cast<float4*>(prow[kk]);
 #pragma unroll
-                    for (int q = 0; q < 8; q++) dst[q] = make_float4(a[i][4 * q], a[i][4 * q + 1], a[i][4 * q + 2], a[i][4 * q + 3]);
+                    for (int q = 0; q < SW / 4; q++) dst[q] = make_float4(a[i][4 * q], a[i][4 * q + 1], a[i][4 * q + 2], a[i][4 * q + 3]);
                     mypos[i] = k;
                 } else if (mypos[i] == k) {
                     mypos[i] = gp;
@@ -490,7 +490,7 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
                     if (act[i]) a[i][kk] = l[i];
                 }
                 const float4* u4 = reinterpret_cast<const float4*>(urow);
-                static_for<(kk + 1) / 4, 8>([&](auto qc) {
+                static_for<(kk + 1) / 4, SW / 4>([&](auto qc) {
                     constexpr int q = decltype(qc)::value;
                     const float4 u = u4[q];
 #pragma unroll
@@ -508,41 +508,43 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
         {
             // M2[physical row][o + cs .. + 31] = the row's 32 registers: transposed through shared memory so that one
             // store instruction writes four complete 128-byte rows instead of a 16-byte piece of thirty-two
-            float* xp = xpose + warp * (32 * 36);
-            float4* mine = reinterpret_cast<float4*>(xp + lane * 36);
-            float* m2b = M2 + b * n * n + o + cs + 4 * (lane & 7);
+            constexpr int XL = SW + 4, PC = SW / 4, RPI = 32 / PC;  // row stride, 16-byte pieces per row, rows per instruction
+            float* xp = xpose + warp * (32 * XL);
+            float4* mine = reinterpret_cast<float4*>(xp + lane * XL);
+            float* m2b = M2 + b * n * n + o + cs + 4 * (lane % PC);
 #pragma unroll
             for (int i = 0; i < RPT; i++) {
                 if (i > 0) __syncwarp();
 #pragma unroll
-                for (int q = 0; q < 8; q++) mine[q] = make_float4(a[i][4 * q], a[i][4 * q + 1], a[i][4 * q + 2], a[i][4 * q + 3]);
+                for (int q = 0; q < PC; q++) mine[q] = make_float4(a[i][4 * q], a[i][4 * q + 1], a[i][4 * q + 2], a[i][4 * q + 3]);
                 __syncwarp();
 #pragma unroll
-                for (int g = 0; g < 8; g++) {
-                    const int row = 4 * g + (lane >> 3);
+                for (int g = 0; g < 32 / RPI; g++) {
+                    const int row = RPI * g + lane / PC;
                     const int row_phys = __shfl_sync(kFull, phys[i], row);
-                    const float4 v = *reinterpret_cast<const float4*>(xp + row * 36 + 4 * (lane & 7));
+                    const float4 v = *reinterpret_cast<const float4*>(xp + row * XL + 4 * (lane % PC));
                     if (warp * 32 + row + i * T < R) *reinterpret_cast<float4*>(m2b + (long)row_phys * n) = v;
                 }
             }
         }
         __syncthreads();  // prow and tw are complete
-        const int rem0 = cs + 32, nrem = NB - rem0;  // panel columns right of the sub-panel
+        const int rem0 = cs + SW, nrem = NB - rem0;  // panel columns right of the sub-panel
         if (nrem > 0) {
             // the new pivot rows in those columns (as they are now: updated by the earlier sub-panels)
             {
-                const int row_t = tw[lane];  // e & 31 == lane for every element e of this thread (blockDim % 32 == 0)
-                for (int e0 = t; e0 < 32 * nrem; e0 += 4 * T) {
+                const int gk = lane % SW;   // e % SW is the same for every element e of this thread (blockDim % 32 == 0)
+                const int row_t = tw[gk];
+                for (int e0 = t; e0 < SW * nrem; e0 += 4 * T) {
                     float g[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const int e = e0 + i * T;
-                        if (e < 32 * nrem) g[i] = pwb[(long)(rem0 + (e >> 5)) * n + row_t];
+                        if (e < SW * nrem) g[i] = pwb[(long)(rem0 + e / SW) * n + row_t];
                     }
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const int e = e0 + i * T;
-                        if (e < 32 * nrem) ublk[lane][e >> 5] = g[i];
+                        if (e < SW * nrem) ublk[gk][e / SW] = g[i];
                     }
                 }
             }
@@ -551,11 +553,12 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
             // three columns, lane j = row j of the block with its multipliers in registers; row kk of the result travels by
             // shuffle, rows below it subtract their multiple of it (right-looking: 32 steps of shuffle + multiply-add)
             {
-                float lrow[32];
+                float lrow[SW];
+                const int lrow_i = lane < SW ? lane : 0;
                 {
-                    const float4* src = reinterpret_cast<const float4*>(prow[lane]);
+                    const float4* src = reinterpret_cast<const float4*>(prow[lrow_i]);
 #pragma unroll
-                    for (int q = 0; q < 8; q++) {
+                    for (int q = 0; q < SW / 4; q++) {
                         const float4 v = src[q];
                         lrow[4 * q] = v.x, lrow[4 * q + 1] = v.y, lrow[4 * q + 2] = v.z, lrow[4 * q + 3] = v.w;
                     }
@@ -563,9 +566,9 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
                 for (int c0 = 3 * warp; c0 < nrem; c0 += 3 * nwarps) {
                     float x[3];
 #pragma unroll
-                    for (int e = 0; e < 3; e++) x[e] = c0 + e < nrem ? ublk[lane][c0 + e] : 0.0f;
+                    for (int e = 0; e < 3; e++) x[e] = (c0 + e < nrem && lane < SW) ? ublk[lrow_i][c0 + e] : 0.0f;
 #pragma unroll
-                    for (int kk = 0; kk < 31; kk++) {
+                    for (int kk = 0; kk < SW - 1; kk++) {
 #pragma unroll
                         for (int e = 0; e < 3; e++) {
                             const float xk = __shfl_sync(kFull, x[e], kk);
@@ -574,7 +577,7 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
                     }
 #pragma unroll
                     for (int e = 0; e < 3; e++)
-                        if (c0 + e < nrem) ublk[lane][c0 + e] = x[e];
+                        if (c0 + e < nrem && lane < SW) ublk[lane][c0 + e] = x[e];
                 }
             }
             __syncthreads();
@@ -605,7 +608,7 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
                             for (int e = 0; e < 4; e++) nx[i][e] = p0[(long)(4 + e) * n + i * T];
                     }
 #pragma unroll
-                    for (int kk = 0; kk < 32; kk++) {
+                    for (int kk = 0; kk < SW; kk++) {
                         const float4 u = *reinterpret_cast<const float4*>(&ublk[kk][4 * c4]);
 #pragma unroll
                         for (int i = 0; i < RPT; i++) {
@@ -623,7 +626,7 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
             }
         }
         // rows o+cs .. o+cs+31 of U inside the panel: zeros | U11 of the sub-panel | its U12
-        for (int e = t; e < 32 * 32; e += T) {
+        for (int e = t; e < SW * 32; e += T) {
             const int kk = e >> 5, q = e & 31;
             float v[4];
 #pragma unroll
@@ -774,13 +777,10 @@ static cudaError_t lu_crout_slice(const float* A, float* L, float* U, int* P, in
         }
         {
             ProfScope ps(HLSD_PROF_PANEL, st);
-            if (option(HLSD_OPT_LU_PANEL_ROWS) == 1) {
-                const int pthreads = std::max(256, n - o);
-                lu_cpanel_kernel<1><<<nb, pthreads, (size_t)(pthreads / 32) * kXposeWarpBytes, st>>>(PWT, M2, U, P, pm(p), pm(p + 1), n, o);
-            } else {
-                const int pthreads = std::max(128, (n - o) / 2);
-                lu_cpanel_kernel<2><<<nb, pthreads, (size_t)(pthreads / 32) * kXposeWarpBytes, st>>>(PWT, M2, U, P, pm(p), pm(p + 1), n, o);
-            }
+            const int pthreads = std::max(128, (n - o) / 2);
+            // measured at N = 1024 (ms per 1024 matrices, all panels): one row per thread 7.75, two rows 6.70, two rows with
+            // 16-column sub-panels (64 registers, two CTAs per SM) 7.11
+            lu_cpanel_kernel<2, 32><<<nb, pthreads, (size_t)(pthreads / 32) * kXposeWarpBytes, st>>>(PWT, M2, U, P, pm(p), pm(p + 1), n, o);
             count_launch();
         }
         if (ct == 0) break;
@@ -816,8 +816,7 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
     if ((e = ensure_dynamic_smem(lu_ll_kernel<LL_COL>, LlSmem::kTotal)) != cudaSuccess) return e;
     if ((e = ensure_dynamic_smem(lu_ll_kernel<LL_ROW>, LlSmem::kTotal)) != cudaSuccess) return e;
     if ((e = ensure_dynamic_smem(lu_trsm_kernel, MmaSmem::kTotal)) != cudaSuccess) return e;
-    if ((e = ensure_dynamic_smem(lu_cpanel_kernel<1>, 32 * kXposeWarpBytes)) != cudaSuccess) return e;
-    if ((e = ensure_dynamic_smem(lu_cpanel_kernel<2>, 16 * kXposeWarpBytes)) != cudaSuccess) return e;
+    if ((e = ensure_dynamic_smem(lu_cpanel_kernel<2, 32>, 16 * kXposeWarpBytes + 16 * 1024)) != cudaSuccess) return e;  // (+ static)
     const long nn = (long)n * n;
     const int panels = n / NB;
     // workspace per matrix: M2, UT (n x n), PWT, T0 (n x 128), W (128 x 128), posmap history; the batch is walked in

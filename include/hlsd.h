@@ -150,7 +150,6 @@ const char* hlsd_version(void);
 #define HLSD_OPT_CHOL_TILE 6    /* exact Cholesky 64 / 128 (right-looking designs): 0 = shared-memory tile kernel blocked by
                                    32 columns (default), 1 = the register kernels of round 1, 2 = tile kernel with 64
                                    instead of 128 threads per 64x64 matrix                                             */
-#define HLSD_OPT_LU_PANEL_ROWS 7 /* tensor LU panel kernel: 0 = two rows per thread (default), 1 = one row per thread         */
 #define HLSD_OPT_COUNT 8
 int hlsd_set_option(int option, int value);
 
