@@ -178,21 +178,19 @@ lu_ll_kernel(const float* __restrict__ A, const float* __restrict__ M2, const fl
         __syncthreads();
         tc_fence_after();
         if (t == 0) {
-            const uint64_t dBhi = make_sw128_desc(smem_u32(rb)), dBlo = make_sw128_desc(smem_u32(lb));
-            const uint64_t dA0hi = make_sw128_desc(smem_u32(ra0)), dA0lo = make_sw128_desc(smem_u32(la0));
-            const uint64_t dA1hi = make_sw128_desc(smem_u32(ra1)), dA1lo = make_sw128_desc(smem_u32(la1));
+            // ONE accumulator of 128 x 256: the shared tile is the M operand, the two paired tiles - contiguous in
+            // shared memory - form one 256-row N operand, so the shared tile is read once per k-step instead of twice
+            // (the kernel is bound by shared-memory bandwidth: 12 KB instead of 16 KB of operand reads per 2 x 262 kflop)
+            const uint64_t dMhi = make_sw128_desc(smem_u32(rb)), dMlo = make_sw128_desc(smem_u32(lb));
+            const uint64_t dNhi = make_sw128_desc(smem_u32(ra0)), dNlo = make_sw128_desc(smem_u32(la0));
+            const uint32_t idesc = two ? kIdescTf32N256 : kIdescTf32;
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) {
                 const uint64_t adv = (uint64_t)((kk * 32) >> 4);
                 const uint32_t first = (c == 0 && kk == 0) ? 0u : 1u;
-                umma_tf32(tmem_d, dA0lo + adv, dBhi + adv, kIdescTf32, first);
-                umma_tf32(tmem_d, dA0hi + adv, dBlo + adv, kIdescTf32, 1u);
-                umma_tf32(tmem_d, dA0hi + adv, dBhi + adv, kIdescTf32, 1u);
-                if (two) {
-                    umma_tf32(tmem_d + 128u, dA1lo + adv, dBhi + adv, kIdescTf32, first);
-                    umma_tf32(tmem_d + 128u, dA1hi + adv, dBlo + adv, kIdescTf32, 1u);
-                    umma_tf32(tmem_d + 128u, dA1hi + adv, dBhi + adv, kIdescTf32, 1u);
-                }
+                umma_tf32(tmem_d, dMlo + adv, dNhi + adv, idesc, first);
+                umma_tf32(tmem_d, dMhi + adv, dNlo + adv, idesc, 1u);
+                umma_tf32(tmem_d, dMhi + adv, dNhi + adv, idesc, 1u);
             }
             umma_commit(&bars[c & 1]);
         }
@@ -203,8 +201,8 @@ lu_ll_kernel(const float* __restrict__ A, const float* __restrict__ M2, const fl
         step(c, 0);
         step(c + 1, 1);
     }
-    // epilogue: thread = accumulator row drow, 32 accumulator columns starting at col; the tile of A is fetched while
-    // the last chunks are still being multiplied
+    // epilogue: thread = accumulator lane drow = row of the SHARED operand tile; accumulator columns h * 128 + col .. + 31 =
+    // rows col .. col + 31 of paired tile h.  The tile of A is fetched while the last chunks are still being multiplied.
     const int drow = (warp & 3) * 32 + lane;
     const int col = (warp >> 2) * 32;
     float cv[2][32];
@@ -212,16 +210,19 @@ lu_ll_kernel(const float* __restrict__ A, const float* __restrict__ M2, const fl
     for (int h = 0; h < 2; h++) {
         if (h == 1 && !two) break;
         if constexpr (MODE == LL_COL) {
-            const float4* src = reinterpret_cast<const float4*>(Ab + (long)pm[o + (t0 + h) * NB + drow] * n + o + col);
+            // lane = column c of the panel, accumulator column j = position (t0 + h) * 128 + col + j: coalesced over c
+            const float* src = Ab + o + drow;
+            const int* pp = pm + o + (t0 + h) * NB + col;
+#pragma unroll
+            for (int j = 0; j < 32; j++) cv[h][j] = __ldg(src + (long)pp[j] * n);
+        } else {
+            // lane = pivot row m, accumulator column j = matrix column o + 128 + (t0 + h) * 128 + col + j
+            const float4* src = reinterpret_cast<const float4*>(Ab + (long)pm[o + drow] * n + o + NB + (t0 + h) * NB + col);
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 const float4 v = __ldg(src + q);
                 cv[h][4 * q] = v.x, cv[h][4 * q + 1] = v.y, cv[h][4 * q + 2] = v.z, cv[h][4 * q + 3] = v.w;
             }
-        } else {
-            const float* src = Ab + o + NB + (t0 + h) * NB + drow;  // column c of A; row pm[o + m] for accumulator column m
-#pragma unroll
-            for (int j = 0; j < 32; j++) cv[h][j] = __ldg(src + (long)pm[o + col + j] * n);
         }
     }
     if (C > 0) {
@@ -240,15 +241,17 @@ lu_ll_kernel(const float* __restrict__ A, const float* __restrict__ M2, const fl
             for (int j = 0; j < 32; j++) acc[j] = 0.0f;
         }
         if constexpr (MODE == LL_COL) {
-            float* dst = out + b * n * NB + (long)col * n + (t0 + h) * NB + drow;  // PWT[c][position - o]
-#pragma unroll
-            for (int j = 0; j < 32; j++) dst[(long)j * n] = cv[h][j] - acc[j];
-        } else {
-            float4* dst = reinterpret_cast<float4*>(out + b * n * NB + (long)((t0 + h) * NB + drow) * NB + col);  // T0[c][m]
+            // PWT[c][position - o]: 32 consecutive positions per thread
+            float4* dst = reinterpret_cast<float4*>(out + b * n * NB + (long)drow * n + (t0 + h) * NB + col);
 #pragma unroll
             for (int q = 0; q < 8; q++)
                 dst[q] = make_float4(cv[h][4 * q] - acc[4 * q], cv[h][4 * q + 1] - acc[4 * q + 1],
                                      cv[h][4 * q + 2] - acc[4 * q + 2], cv[h][4 * q + 3] - acc[4 * q + 3]);
+        } else {
+            // T0[c][m]: coalesced over m
+            float* dst = out + b * n * NB + (long)((t0 + h) * NB + col) * NB + drow;
+#pragma unroll
+            for (int j = 0; j < 32; j++) dst[(long)j * NB] = cv[h][j] - acc[j];
         }
     }
     tc_fence_before();

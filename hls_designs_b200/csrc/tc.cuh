@@ -67,6 +67,8 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, M = 128, N = 128
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// the same with N = 256
+constexpr uint32_t kIdescTf32N256 = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
