@@ -685,21 +685,20 @@ blk_ll2_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q)
         __syncthreads();
         tc_fence_after();
         if (t == 0) {
-            const uint64_t dBhi = make_sw128_desc(smem_u32(rb)), dBlo = make_sw128_desc(smem_u32(lb));
-            const uint64_t dA0hi = make_sw128_desc(smem_u32(ra0)), dA0lo = make_sw128_desc(smem_u32(la0));
-            const uint64_t dA1hi = make_sw128_desc(smem_u32(ra1)), dA1lo = make_sw128_desc(smem_u32(la1));
+            // ONE accumulator of 128 x 256 (transposed result): block row q's tile is the M operand, the two paired row
+            // tiles - contiguous in shared memory - form one 256-row N operand, so the shared tile is read once per
+            // k-step instead of twice (shared-memory bandwidth bounds this kernel: 12 KB instead of 16 KB of operand
+            // reads per pair of 128 x 128 x 8 products)
+            const uint64_t dMhi = make_sw128_desc(smem_u32(rb)), dMlo = make_sw128_desc(smem_u32(lb));
+            const uint64_t dNhi = make_sw128_desc(smem_u32(ra0)), dNlo = make_sw128_desc(smem_u32(la0));
+            const uint32_t idesc = two ? kIdescTf32N256 : kIdescTf32;
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) {
                 const uint64_t adv = (uint64_t)((kk * 32) >> 4);
                 const uint32_t first = (c == 0 && kk == 0) ? 0u : 1u;
-                umma_tf32(tmem_d, dA0lo + adv, dBhi + adv, kIdescTf32, first);
-                umma_tf32(tmem_d, dA0hi + adv, dBlo + adv, kIdescTf32, 1u);
-                umma_tf32(tmem_d, dA0hi + adv, dBhi + adv, kIdescTf32, 1u);
-                if (two) {
-                    umma_tf32(tmem_d + 128u, dA1lo + adv, dBhi + adv, kIdescTf32, first);
-                    umma_tf32(tmem_d + 128u, dA1hi + adv, dBlo + adv, kIdescTf32, 1u);
-                    umma_tf32(tmem_d + 128u, dA1hi + adv, dBhi + adv, kIdescTf32, 1u);
-                }
+                umma_tf32(tmem_d, dMlo + adv, dNhi + adv, idesc, first);
+                umma_tf32(tmem_d, dMhi + adv, dNlo + adv, idesc, 1u);
+                umma_tf32(tmem_d, dMhi + adv, dNhi + adv, idesc, 1u);
             }
             umma_commit(&bars[c & 1]);
         }
@@ -710,16 +709,19 @@ blk_ll2_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q)
         step(c, 0);
         step(c + 1, 1);
     }
-    // the C tiles (from A) are fetched while the last chunks are still being multiplied
-    const long coff = (long)r0 * NB * n + (long)q * NB;
-    constexpr int kRowsPerWarp = 8;
-    float4 cv[2][kRowsPerWarp];
+    // epilogue.  The accumulator holds the TRANSPOSED tiles: lane = column c of block column q, accumulator column
+    // h * 128 + j = row j of row tile r0 + h.  For a fixed row the 32 lanes of a warp cover 32 consecutive columns, so C
+    // is read from A and X written to L with coalesced 128-byte accesses straight from / to registers.  The C values are
+    // fetched while the last chunks are still being multiplied.
+    const int dlane = (warp & 3) * 32 + lane;  // column within the block column
+    const int rbase = (warp >> 2) * 32;        // 32 rows of each tile
+    const long coff = (long)r0 * NB * n + (long)q * NB + dlane;
+    float cv[2][32];
 #pragma unroll
     for (int h = 0; h < 2; h++)
         if (h == 0 || two) {
 #pragma unroll
-            for (int rr = 0; rr < kRowsPerWarp; rr++)
-                cv[h][rr] = *(reinterpret_cast<const float4*>(Sb + coff + (long)(h * NB + warp * kRowsPerWarp + rr) * n) + lane);
+            for (int j = 0; j < 32; j++) cv[h][j] = __ldg(Sb + coff + (long)(h * NB + rbase + j) * n);
         }
     mbar_wait(&bars[(C - 2) & 1], (uint32_t)(((C - 2) >> 1) & 1));
     mbar_wait(&bars[(C - 1) & 1], (uint32_t)(((C - 1) >> 1) & 1));
@@ -727,31 +729,10 @@ blk_ll2_kernel(const float* __restrict__ S, float* __restrict__ L, int n, int q)
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         if (h == 1 && !two) break;
-        float* stage = reinterpret_cast<float*>(smem) + h * (128 * 128);
-        const int drow = (warp & 3) * 32 + lane;
-        const int col = (warp >> 2) * 32;
         float acc[32];
-        tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(h * 128 + col), acc);
+        tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(h * 128 + rbase), acc);
 #pragma unroll
-        for (int qq = 0; qq < 8; qq++) {
-            const int c4 = (col >> 2) + qq;
-            *reinterpret_cast<float4*>(stage + drow * 128 + ((c4 ^ (drow & 7)) << 2)) =
-                make_float4(acc[4 * qq], acc[4 * qq + 1], acc[4 * qq + 2], acc[4 * qq + 3]);
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        if (h == 1 && !two) break;
-        const float* stage = reinterpret_cast<const float*>(smem) + h * (128 * 128);
-#pragma unroll
-        for (int rr = 0; rr < kRowsPerWarp; rr++) {
-            const int row = warp * kRowsPerWarp + rr;
-            const float4 d = *reinterpret_cast<const float4*>(stage + row * 128 + ((lane ^ (row & 7)) << 2));
-            float4 v = cv[h][rr];
-            v.x -= d.x, v.y -= d.y, v.z -= d.z, v.w -= d.w;
-            *(reinterpret_cast<float4*>(Lb + coff + (long)(h * NB + row) * n) + lane) = v;
-        }
+        for (int j = 0; j < 32; j++) Lb[coff + (long)(h * NB + rbase + j) * n] = cv[h][j] - acc[j];
     }
     tc_fence_before();
     __syncthreads();
