@@ -356,6 +356,7 @@ lu_regs_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
 // ------------------------------------------------------------------------------------------------
 // LOCKSTEP: the per-matrix barrier becomes a CTA-wide one, so that all matrices of a CTA walk through the unrolled
 // code together (see chol_rows_kernel: instruction fetch is the top stall of the 128 x 128 kernel).
+constexpr int kDirectLoadMaxN = 128;
 template <int N, int MATS, bool PIVOT, bool FUSED, bool LOCKSTEP = false>
 __global__ void __launch_bounds__(MATS * N, 1)
 lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __restrict__ U, int* __restrict__ P,
@@ -366,6 +367,7 @@ lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
     constexpr int kPerMat = N * LD + 2 * WPM * N + N + 4 * WPM;  // floats: slab, row slots, P, candidates
     static_assert((N * LD) % 4 == 0 && kPerMat % 4 == 0, "16-byte alignment of the pieces");
     constexpr uint32_t kRowBytes = N * 4;
+    constexpr bool kDirectLoad = N <= kDirectLoadMaxN;  // operand rows straight from global memory into registers
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* base = reinterpret_cast<float*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)MATS * kPerMat * 4);
@@ -391,15 +393,26 @@ lu_lane_kernel(const float* __restrict__ A, float* __restrict__ L, float* __rest
         const bool live = b < batch;  // (LOCKSTEP: idle matrices of the last round keep step with the others)
         if (!LOCKSTEP && !live) break;
         bulk_wait_read<0>();   // the previous matrix's P has left
-        fence_async_smem();    // ... and its slab was read with ordinary loads: order them before the bulk copies below
-        gsync();
-        if (r == 0) mbar_arrive_expect_tx(bar, live ? N * kRowBytes : 0);
-        gsync();
-        if (live) bulk_g2s(sA + r * N, A + b * (long)(N * N) + r * N, kRowBytes, bar);
-        mbar_wait(bar, parity);
-        parity ^= 1;
         float a[N];
-        {
+        if constexpr (kDirectLoad) {
+            // N = 32: every lane reads its own 128-byte row straight into registers.  ncu on the staged version: the
+            // proxy fence in front of the bulk copies was the top stall line (10 % of the samples, `membar`), and with 32
+            // warps per SM nothing is gained by staging
+            gsync();
+            const float4* g4 = reinterpret_cast<const float4*>(A + b * (long)(N * N) + r * N);
+#pragma unroll
+            for (int q = 0; q < N / 4; q++) {
+                const float4 v = live ? __ldg(g4 + q) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                a[4 * q] = v.x, a[4 * q + 1] = v.y, a[4 * q + 2] = v.z, a[4 * q + 3] = v.w;
+            }
+        } else {
+            fence_async_smem();    // ... and its slab was read with ordinary loads: order them before the bulk copies below
+            gsync();
+            if (r == 0) mbar_arrive_expect_tx(bar, live ? N * kRowBytes : 0);
+            gsync();
+            if (live) bulk_g2s(sA + r * N, A + b * (long)(N * N) + r * N, kRowBytes, bar);
+            mbar_wait(bar, parity);
+            parity ^= 1;
             const float4* row4 = reinterpret_cast<const float4*>(sA + r * N);
 #pragma unroll
             for (int q = 0; q < N / 4; q++) {
