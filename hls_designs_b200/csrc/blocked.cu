@@ -867,7 +867,7 @@ __device__ __forceinline__ PivCand piv_better(PivCand a, PivCand b) {
 // and with the exact U12 / trailing-update kernels of blocked_exact.cu the whole factorisation - is bit-identical.
 template <bool EXACT>
 __global__ void __launch_bounds__(1024, 1)
-lu_panel_kernel(float* __restrict__ Wk, float* __restrict__ L, int* __restrict__ P, int n, int o) {
+lu_panel_kernel(float* __restrict__ Wk, float* __restrict__ L, int* __restrict__ P, int n, int o, int pivoting) {
     // double buffered by column parity: two barriers per column are enough (after the search partials, after the
     // pivot row is published); a warp that runs ahead into the next column writes the other buffers
     __shared__ float urow_b[2][32];  // pivot row, columns kk.. of the sub-panel
@@ -903,7 +903,7 @@ lu_panel_kernel(float* __restrict__ Wk, float* __restrict__ L, int* __restrict__
             int p = k;
             float* urow = urow_b[kk & 1];
             float* krow = krow_b[kk & 1];
-            if (k < n - 1) {
+            if (k < n - 1 && pivoting) {  // (HLSD_LU_NOPIVOT: P[k] = k, no search)
                 PivCand* red = red_b[kk & 1];
                 PivCand c{-2.0f, 0x7fffffff};
                 if (live && row >= k) {
@@ -1159,7 +1159,7 @@ cudaError_t lu_inverse_l11(const float* M2, const int* posmap, float* W, int n, 
 // trailing update on SIMT tiles (blocked_exact.cu).  Bit-identical to the csim: L, U and P.
 cudaError_t xlu_u12_and_update(float* Wk, const float* L, int n, int o, long batch, cudaStream_t st);  // blocked_exact.cu
 
-cudaError_t lu_blocked_exact(const float* A, float* L, float* U, int* P, int n, long batch, cudaStream_t st) {
+cudaError_t lu_blocked_exact(const float* A, float* L, float* U, int* P, int n, long batch, int pivoting, cudaStream_t st) {
     if (n % NB != 0 || n < 2 * NB || n > 1024) return cudaErrorNotSupported;
     if ((((uintptr_t)A | (uintptr_t)L | (uintptr_t)U) & 15) != 0) return cudaErrorNotSupported;
     if (batch == 0) return cudaSuccess;
@@ -1185,18 +1185,18 @@ cudaError_t lu_blocked_exact(const float* A, float* L, float* U, int* P, int n, 
         const int ncols = (panels - p - 1) * NB;
         {
             ProfScope ps(HLSD_PROF_PANEL, st);
-            lu_panel_kernel<true><<<nb, std::max(256, n - o), 0, st>>>(U, L, P, n, o);
+            lu_panel_kernel<true><<<nb, std::max(256, n - o), 0, st>>>(U, L, P, n, o, pivoting);
             count_launch();
         }
         if (ncols > 0) {
-            {
+            if (pivoting) {
                 ProfScope ps(HLSD_PROF_PERMUTE, st);
                 lu_swap_kernel<<<dim3((ncols + 127) / 128, nb), 128, n * sizeof(int), st>>>(U, P, n, o);
                 count_launch();
             }
             if ((e = xlu_u12_and_update(U, L, n, o, batch, st)) != cudaSuccess) return e;
         }
-        {
+        if (pivoting) {
             ProfScope ps(HLSD_PROF_PERMUTE, st);
             lu_unswap_panel_kernel<<<nb, kUnswapThreads, unswap_smem, st>>>(L, P, n, o);  // L21 has served as operand
             count_launch();

@@ -195,18 +195,17 @@ static int lu_dev(const float* A, float* L, float* U, int32_t* P, int n, int64_t
     if (n < 1 || batch < 0) return fail(HLSD_ERR_INVALID, "n must be >= 1 and batch >= 0");
     if (!lu_pivoting(design, &pivoting)) return fail(HLSD_ERR_INVALID, "unknown LU design");
     if (int rc = check_flags(flags, &path, &exact, &fused)) return rc;
-    if (path == HLSD_PATH_AUTO && pivoting && n >= 256 && n <= 1024 && n % 128 == 0 &&
+    if (path == HLSD_PATH_AUTO && n >= 256 && n <= 1024 && n % 128 == 0 &&
         (((uintptr_t)A | (uintptr_t)L | (uintptr_t)U) & 15) == 0)
         path = exact ? HLSD_PATH_BLOCKED : HLSD_PATH_TENSOR;  // both blocked; BLOCKED keeps the csim's bits
     if (path == HLSD_PATH_TENSOR || path == HLSD_PATH_BLOCKED) {
-        if (!pivoting) return fail(HLSD_ERR_UNSUPPORTED, "the blocked LU implements the pivoted designs only");
         cudaError_t e = cudaSuccess;
         const int64_t kSlice = 32768;
         for (int64_t b0 = 0; b0 < batch && e == cudaSuccess; b0 += kSlice) {
             const int64_t cnt = batch - b0 < kSlice ? batch - b0 : kSlice;
             e = path == HLSD_PATH_TENSOR
-                    ? lu_blocked(A + b0 * n * n, L + b0 * n * n, U + b0 * n * n, P + b0 * n, n, (long)cnt, st)
-                    : lu_blocked_exact(A + b0 * n * n, L + b0 * n * n, U + b0 * n * n, P + b0 * n, n, (long)cnt, st);
+                    ? lu_blocked(A + b0 * n * n, L + b0 * n * n, U + b0 * n * n, P + b0 * n, n, (long)cnt, pivoting, st)
+                    : lu_blocked_exact(A + b0 * n * n, L + b0 * n * n, U + b0 * n * n, P + b0 * n, n, (long)cnt, pivoting, st);
         }
         if (e == cudaErrorNotSupported) return fail(HLSD_ERR_UNSUPPORTED, "the blocked LU paths need n % 128 == 0, 256 <= n <= 1024 and 16-byte aligned buffers");
         if (e != cudaSuccess) return cuda_fail(e, "lu_blocked");

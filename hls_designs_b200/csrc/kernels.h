@@ -56,10 +56,10 @@ cudaError_t cholesky128_exact(const float* A, float* L, long batch, int fused, c
 
 // Blocked LU with partial pivoting on the tensor cores (n % 128 == 0, 256 <= n <= 1024): Crout order, rows never
 // moved (lu_crout.cu).
-cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long batch, cudaStream_t st);
+cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long batch, int pivoting, cudaStream_t st);
 
 // The same factorisation in the reference's exact arithmetic and per-element order (bit-identical L, U, P).
-cudaError_t lu_blocked_exact(const float* A, float* L, float* U, int* P, int n, long batch, cudaStream_t st);
+cudaError_t lu_blocked_exact(const float* A, float* L, float* U, int* P, int n, long batch, int pivoting, cudaStream_t st);
 
 // Self-check: shared-divisor division (common.cuh) vs IEEE division over `count` device-resident pairs;
 // out[0] = bitwise mismatches, out[1] = pairs served by the fast path, out[2] = mismatches of the unguarded

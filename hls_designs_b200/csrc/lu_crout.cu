@@ -398,7 +398,7 @@ constexpr int kXposeWarpBytes = 32 * 36 * 4;  // dynamic shared memory of lu_cpa
 template <int RPT, int SW>
 __global__ void __launch_bounds__(1024 / RPT, SW == 16 ? 2 : 1)
 lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restrict__ U, int* __restrict__ P,
-                 const int* __restrict__ pm_in, int* __restrict__ pm_out, int n, int o) {
+                 const int* __restrict__ pm_in, int* __restrict__ pm_out, int n, int o, int pivoting) {
     __shared__ __align__(16) float slot[2][32][SW];  // speculative pivot rows, one per warp
     __shared__ PCand cand[2][32];
     __shared__ __align__(16) float prow[SW][SW + 4];     // pivot rows of the sub-panel: multipliers | U11
@@ -437,6 +437,7 @@ lu_cpanel_kernel(float* __restrict__ PWT, float* __restrict__ M2, float* __restr
                 if (mypos[i] >= k) {
                     const float v = fabsf(a[i][kk]);
                     key = (v != v) ? (mypos[i] == k ? 0x7f800001u : 0u) : __float_as_uint(v) + 1u;
+                    if (!pivoting) key = mypos[i] == k ? 1u : 0u;  // HLSD_LU_NOPIVOT: the row at position k is the only candidate
                 }
                 if (key > kb || (key == kb && key != 0u && mypos[i] < pb)) kb = key, pb = mypos[i];
             }
@@ -750,7 +751,7 @@ lu_assemble_l_kernel(const float* __restrict__ M2, float* __restrict__ L, const 
 // W = inv(L11) through posmap: blocked.cu
 cudaError_t lu_inverse_l11(const float* M2, const int* posmap, float* W, int n, int o, long batch, cudaStream_t st);
 
-static cudaError_t lu_crout_slice(const float* A, float* L, float* U, int* P, int n, long batch, float* ws, cudaStream_t st) {
+static cudaError_t lu_crout_slice(const float* A, float* L, float* U, int* P, int n, long batch, int pivoting, float* ws, cudaStream_t st) {
     const long nn = (long)n * n;
     const int panels = n / NB;
     float* M2 = ws;
@@ -783,7 +784,7 @@ static cudaError_t lu_crout_slice(const float* A, float* L, float* U, int* P, in
             const int pthreads = std::max(128, (n - o) / 2);
             // measured at N = 1024 (ms per 1024 matrices, all panels): one row per thread 7.75, two rows 6.70, two rows with
             // 16-column sub-panels (64 registers, two CTAs per SM) 7.11
-            lu_cpanel_kernel<2, 32><<<nb, pthreads, (size_t)(pthreads / 32) * kXposeWarpBytes, st>>>(PWT, M2, U, P, pm(p), pm(p + 1), n, o);
+            lu_cpanel_kernel<2, 32><<<nb, pthreads, (size_t)(pthreads / 32) * kXposeWarpBytes, st>>>(PWT, M2, U, P, pm(p), pm(p + 1), n, o, pivoting);
             count_launch();
         }
         if (ct == 0) break;
@@ -811,7 +812,7 @@ static cudaError_t lu_crout_slice(const float* A, float* L, float* U, int* P, in
     return cudaGetLastError();
 }
 
-cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long batch, cudaStream_t st) {
+cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long batch, int pivoting, cudaStream_t st) {
     if (n % NB != 0 || n < 2 * NB || n > 1024) return cudaErrorNotSupported;
     if ((((uintptr_t)A | (uintptr_t)L | (uintptr_t)U) & 15) != 0) return cudaErrorNotSupported;
     if (batch == 0) return cudaSuccess;
@@ -830,7 +831,7 @@ cudaError_t lu_blocked(const float* A, float* L, float* U, int* P, int n, long b
     if ((e = ws_alloc(reinterpret_cast<void**>(&ws), per_mat * (size_t)slice, st)) != cudaSuccess) return e;
     for (long b0 = 0; b0 < batch && e == cudaSuccess; b0 += slice) {
         const long cnt = std::min(slice, batch - b0);
-        e = lu_crout_slice(A + b0 * nn, L + b0 * nn, U + b0 * nn, P + b0 * n, n, cnt, ws, st);
+        e = lu_crout_slice(A + b0 * nn, L + b0 * nn, U + b0 * nn, P + b0 * n, n, cnt, pivoting, ws, st);
     }
     ws_free(ws, st);
     return e;

@@ -202,8 +202,12 @@ def test_blocked_exact_lu_vs_oracle(n, batch):
     got_d = hd.lu(torch.from_numpy(A).cuda(), path="blocked")
     for g, w in zip(got_d, restate.lu(A, threads=8)):
         assert bits_equal(g.cpu().numpy(), w)
-    with pytest.raises(hd.HlsdError):
-        hd.lu(A, design="nopivot", path="blocked")
+    # HLSD_LU_NOPIVOT (this library's unpivoted variant, P[k] = k) through the same blocked exact path: bit-identical to
+    # the oracle's unpivoted elimination (a diagonally dominant operand keeps it finite)
+    D = (A[:2] + np.float32(200 * A.shape[-1]) * np.eye(A.shape[-1], dtype=np.float32)).astype(np.float32)
+    for kw in (dict(path="blocked"), dict(exact=True)):
+        for g, w in zip(hd.lu(D, design="nopivot", **kw), restate.lu(D, pivoting=False, threads=8)):
+            assert bits_equal(g, w), f"nopivot {kw}: {first_mismatch(g, w)}"
 
 
 # ---------------------------------------------------------------- HLSD_FLAG_FUSED (opt-in contraction)

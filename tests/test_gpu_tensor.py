@@ -94,6 +94,22 @@ def test_tensor_lu_vs_oracle(n, batch):
         assert P[:, 0].tolist() == want[2][:, 0].tolist()  # first column: no arithmetic yet, pivots must agree
 
 
+@pytest.mark.parametrize("n", (256, 512))
+def test_tensor_lu_unpivoted(n):
+    """HLSD_LU_NOPIVOT on the tensor path (auto dispatch at n >= 256): P[k] = k, residual and element-wise agreement with the
+    oracle's unpivoted elimination on a diagonally dominant operand."""
+    from conftest import lu_residual
+    from hls_designs_b200.operand import gen_full_rank
+    A = (gen_full_rank(n, batch=3, seed=n) + np.float32(100 * n) * np.eye(n, dtype=np.float32)).astype(np.float32)
+    L, U, P = hd.lu(A, design="nopivot")
+    wl, wu, wp = restate.lu(A, pivoting=False, threads=8)
+    assert np.array_equal(P, wp) and np.array_equal(P[0], np.arange(n))
+    for b in range(3):
+        assert np.abs(np.triu(L[b], 1)).max() == 0.0 and np.abs(np.tril(U[b], -1)).max() == 0.0
+        assert lu_residual(A[b], L[b], U[b], P[b]) < 5e-5
+        assert np.abs(L[b] - wl[b]).max() < 1e-3 and np.abs(U[b] - wu[b]).max() / np.abs(wu[b]).max() < 1e-3
+
+
 def test_full_size_tensor_paths_n1024_properties():
     """configs[4] (N = 1024) on a 256-matrix slice of the batch: residuals on the device for EVERY matrix, structure of
     the factors, and twelve matrices spread over the slice against the oracle within the documented tolerances (tensor
