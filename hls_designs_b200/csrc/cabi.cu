@@ -250,7 +250,11 @@ struct Buf {
 // leak nothing.  Buffers above kKeepBytes are dropped when the call ends instead of being kept.
 struct Workspace {
     static constexpr int kStreams = 3;
-    static constexpr size_t kKeepBytes = (size_t)256 << 20;
+    // Staging buffers above this size are freed when a call ends (a 4096 x 4096 matrix must not pin gigabytes for ever).
+    // It was 256 MB, which made every hlsd_lu_host / hlsd_cholesky_host call at n = 1024 free and re-allocate its 0.6 GB
+    // chunk buffers (bench: the LU-1024 host leg ran at half the rate of a copy-only pass with small records); a chunk
+    // of one matrix per SM at n = 1024 now stays.  hlsd_release_workspace() still frees everything.
+    static constexpr size_t kKeepBytes = (size_t)1536 << 20;
     int device = -1;
     cudaStream_t st[kStreams] = {};
     std::vector<void*> buf[kStreams];

@@ -138,7 +138,8 @@ lu_ll_kernel(const float* __restrict__ A, const float* __restrict__ M2, const fl
         const int row = it * 64 + (t >> 3), c4 = t & 7;
         return row * 128 + ((c4 ^ (row & 7)) << 4);
     };
-    float4 b0[2][2], b1[2][2], bb[2][2];  // [register stage][piece]: A0, A1, B
+    constexpr int kPre = 3;  // chunks of global loads in flight per thread (register stages)
+    float4 b0[kPre][2], b1[kPre][2], bb[kPre][2];  // [register stage][piece]: A0, A1, B
     auto gload = [&](int c, int sreg) {
         if (c < C) {
 #pragma unroll
@@ -172,7 +173,7 @@ lu_ll_kernel(const float* __restrict__ A, const float* __restrict__ M2, const fl
             *reinterpret_cast<float4*>(rb + off) = bb[sreg][it];
             *reinterpret_cast<float4*>(lb + off) = lo_of(bb[sreg][it]);
         }
-        gload(c + 2, sreg);
+        gload(c + kPre, sreg);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -195,11 +196,15 @@ lu_ll_kernel(const float* __restrict__ A, const float* __restrict__ M2, const fl
             umma_commit(&bars[c & 1]);
         }
     };
+    // three chunks of loads in flight (ncu: with two, `long_scoreboard` was the top stall and DRAM and the tensor pipe
+    // both sat near 50 %): the register stage is c % 3 (static), the shared-memory stage c % 2
     gload(0, 0);
     gload(1, 1);
-    for (int c = 0; c < C; c += 2) {
+    gload(2, 2);
+    for (int c = 0; c < C; c += 3) {
         step(c, 0);
-        step(c + 1, 1);
+        if (c + 1 < C) step(c + 1, 1);
+        if (c + 2 < C) step(c + 2, 2);
     }
     // epilogue: thread = accumulator lane drow = row of the SHARED operand tile; accumulator columns h * 128 + col .. + 31 =
     // rows col .. col + 31 of paired tile h.  The tile of A is fetched while the last chunks are still being multiplied.
