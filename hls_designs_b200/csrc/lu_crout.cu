@@ -788,7 +788,11 @@ static cudaError_t lu_crout_slice(const float* A, float* L, float* U, int* P, in
             ProfScope ps(HLSD_PROF_PANEL, st);
             const int pthreads = std::max(128, (n - o) / 2);
             // measured at N = 1024 (ms per 1024 matrices, all panels): one row per thread 7.75, two rows 6.70, two rows with
-            // 16-column sub-panels (64 registers, two CTAs per SM) 7.11
+            // 16-column sub-panels (64 registers, two CTAs per SM) 7.11; the rank-32 update between sub-panels on the tensor
+            // core (each thread's 32 multipliers = one swizzle-atom row of a 128-row operand tile, N = remaining columns,
+            // product read back from TMEM and subtracted with RED, one pipeline per group of four warps): correct, 30 % fewer
+            // instructions, and 7.59 - instruction fetch (`no_instruction` 3.1 warps per issue) and the serial
+            // write/MMA/read-back rounds cost more than the 3000 FFMAs per row they replace
             lu_cpanel_kernel<2, 32><<<nb, pthreads, (size_t)(pthreads / 32) * kXposeWarpBytes, st>>>(PWT, M2, U, P, pm(p), pm(p + 1), n, o, pivoting);
             count_launch();
         }
