@@ -110,6 +110,27 @@ def test_tensor_lu_unpivoted(n):
         assert np.abs(L[b] - wl[b]).max() < 1e-3 and np.abs(U[b] - wu[b]).max() / np.abs(wu[b]).max() < 1e-3
 
 
+def test_tensor_lu_workspace_slices():
+    """The tensor LU walks a large batch in slices that bound its workspace (18 GB; lu_crout.cu): a batch that needs two
+    slices gives, matrix for matrix, the results of separate calls on its parts, and valid factorisations in both."""
+    import torch
+    n, batch = 256, 24000  # 0.84 MB of workspace per matrix -> 23 011 matrices per slice
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.randint(1, 101, (batch, n, n), generator=g, device="cuda").float()
+    L, U, P = hd.lu(A)
+    head = slice(0, 64)
+    tail = slice(batch - 700, batch)  # inside the second slice
+    for part in (head, tail):
+        Lp, Up, Pp = hd.lu(A[part].contiguous())
+        assert torch.equal(Lp, L[part]) and torch.equal(Up, U[part]) and torch.equal(Pp, P[part])
+    # P[k] >= k everywhere, unit lower / upper structure on a sample from both slices
+    assert bool((P >= torch.arange(n, device="cuda", dtype=P.dtype)).all()) and bool((P < n).all())
+    pick = torch.tensor([0, 1, 22999, 23011, 23012, batch - 1], device="cuda")
+    from conftest import lu_residual
+    for b in pick.tolist():
+        assert lu_residual(A[b].cpu().numpy(), L[b].cpu().numpy(), U[b].cpu().numpy(), P[b].cpu().numpy()) < 5e-5
+
+
 def test_full_size_tensor_paths_n1024_properties():
     """configs[4] (N = 1024) on a 256-matrix slice of the batch: residuals on the device for EVERY matrix, structure of
     the factors, and twelve matrices spread over the slice against the oracle within the documented tolerances (tensor
