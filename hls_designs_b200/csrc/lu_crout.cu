@@ -802,6 +802,12 @@ static cudaError_t lu_crout_slice(const float* A, float* L, float* U, int* P, in
             cudaError_t e = lu_inverse_l11(M2, pm(p + 1), W, n, o, batch, st);
             if (e != cudaSuccess) return e;
         }
+        // Measured alternatives of the long-K kernels (ms per 1024 matrices, both forms, all panels; default 5.24 + 1.27 for
+        // the solve): the solve U12 = W X12 fused into this kernel's epilogue (X12 written to shared memory as the N operand
+        // of a second product, K in two halves) 6.85 - with one CTA per SM nothing overlaps the serial epilogue; 256
+        // threads, one shared-memory stage, two CTAs per SM 6.45 - the overlap of a CTA's own stores with its own MMAs is
+        // worth more than a second CTA; two instead of three chunks of loads in flight 5.32; two 128 x 128 accumulators
+        // instead of one 128 x 256 5.39.
         {
             ProfScope ps(HLSD_PROF_UPDATE, st);
             lu_ll_kernel<LL_ROW><<<dim3((ct + 1) / 2, nb), 512, LlSmem::kTotal, st>>>(A, M2, UT, pm(p + 1), T0, n, o);
