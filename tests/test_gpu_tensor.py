@@ -110,6 +110,24 @@ def test_tensor_lu_unpivoted(n):
         assert np.abs(L[b] - wl[b]).max() < 1e-3 and np.abs(U[b] - wu[b]).max() / np.abs(wu[b]).max() < 1e-3
 
 
+@pytest.mark.parametrize("n", (384, 640, 768, 896))
+def test_tensor_lu_other_multiples_of_128(n):
+    """Panel heights that are not powers of two (block sizes 192, 320, 384, 448 threads in the panel kernel, odd tile counts
+    in the long-K kernels): same pivots as the csim on integer operands, residual, element-wise tolerance."""
+    from conftest import lu_elementwise_ok, lu_residual
+    from hls_designs_b200.operand import gen_full_rank
+    A = gen_full_rank(n, batch=2, seed=n + 1)
+    L, U, P = hd.lu(A, path="tensor")
+    wl, wu, wp = restate.lu(A, threads=8)
+    for b in range(2):
+        assert np.abs(np.triu(L[b], 1)).max() == 0.0 and np.abs(np.tril(U[b], -1)).max() == 0.0 and np.allclose(np.diag(L[b]), 1.0)
+        assert lu_residual(A[b], L[b], U[b], P[b]) < 5e-5
+        if np.array_equal(P[b], wp[b]):
+            ok, detail = lu_elementwise_ok(A[b], L[b], U[b], P[b], wl[b], wu[b])
+            assert ok, detail
+    assert any(np.array_equal(P[b], wp[b]) for b in range(2)), "no pivot sequence equal to the csim's"
+
+
 def test_tensor_lu_workspace_slices():
     """The tensor LU walks a large batch in slices that bound its workspace (18 GB; lu_crout.cu): a batch that needs two
     slices gives, matrix for matrix, the results of separate calls on its parts, and valid factorisations in both."""
