@@ -528,6 +528,7 @@ qr_wave_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __rest
 // halves the threads and registers a matrix occupies: two (128 x 128) or more CTAs share an SM, and one matrix's
 // angle generation and barrier waits are filled by another matrix's rotations.  (ncu on the two-role kernel at
 // 128 x 128, one CTA per SM: issue slots 45 % busy, `barrier` + `wait` the top stalls.)
+// (three CTAs per SM at N = 128 - a 168-register cap - spill the Q row in the slot loop: 683 k -> 299 k fact/s)
 template <int N, int RT, bool FUSED, bool UNI = false>
 __global__ void __launch_bounds__(UNI ? N : RT + N, UNI ? (N == 64 ? 8 : 2) : (N == 64 ? 4 : 1))
 qr_qreg_kernel(const float* __restrict__ A, float* __restrict__ Q, float* __restrict__ R, long batch) {
