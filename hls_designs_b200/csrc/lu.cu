@@ -709,6 +709,7 @@ static cudaError_t lu_dispatch(const float* A, float* L, float* U, int* P, int n
     const bool aligned = (((uintptr_t)A | (uintptr_t)L | (uintptr_t)U | (uintptr_t)P) & 15) == 0;
     if (path == HLSD_PATH_AUTO || path == HLSD_PATH_TPM) {
         if (aligned && n == 4) return launch_lu_tpm<4, FUSED>(A, L, U, P, batch, pivoting, st);
+        // (thread-per-matrix at N = 8 - 148 registers, pivot exchanges as predicated swaps - measured 4.5 G against 5.2 G fact/s)
         if (aligned && n == 8) return launch_lu_regs<8, 2, 20, FUSED>(A, L, U, P, batch, pivoting, st);
         if (aligned && n == 16) return launch_lu_regs<16, 4, 12, FUSED, true>(A, L, U, P, batch, pivoting, st);  // U rows straight out: +10 %
         if (aligned && n == 32) {
