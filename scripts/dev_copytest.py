@@ -1,19 +1,43 @@
-import sys, time, ctypes, numpy as np
-sys.path.insert(0, "/root/repo")
+#!/usr/bin/env python3
+"""The host staging pipeline without kernels (hlsd_selftest_copy_host): record shapes, and input buffers allocated as
+plain pinned vs write-combined pinned memory.  python scripts/dev_copytest.py"""
+import ctypes
+import os
+import sys
+import time
+
 import torch
-import hls_designs_b200 as hd
-from hls_designs_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from hls_designs_b200 import _lib  # noqa: E402
+
 lib = _lib.load()
-lib.hlsd_host_alloc.restype = ctypes.c_void_p
 lib.hlsd_selftest_copy_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int64]
 torch.cuda.init()
-n, batch = 1024, 682
-in_mat, out_mat = n * n * 4, 2 * n * n * 4 + n * 4
-pa = lib.hlsd_host_alloc(ctypes.c_size_t(in_mat * batch)); po = lib.hlsd_host_alloc(ctypes.c_size_t(out_mat * batch))
-for shape in ((in_mat, out_mat), (in_mat, in_mat), (in_mat // 2, out_mat // 2), (64 << 10, 128 << 10)):
-    units = batch * in_mat // shape[0]
-    for it in range(4):
+rt = ctypes.CDLL("libcudart.so.12")  # the runtime torch has already loaded
+rt.cudaHostAlloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t, ctypes.c_uint]
+rt.cudaFreeHost.argtypes = [ctypes.c_void_p]
+size = 1 << 30
+
+
+def alloc(flags):
+    ptr = ctypes.c_void_p()
+    err = rt.cudaHostAlloc(ctypes.byref(ptr), size, flags)
+    assert err == 0, err
+    return ptr.value
+
+
+po = alloc(0)
+for name, flags in (("pinned", 0), ("write-combined", 4), ("pinned", 0), ("write-combined", 4)):
+    pa = alloc(flags)
+    ctypes.memset(pa, 1, size)
+    lib.hlsd_selftest_copy_host(pa, po, 2048, 2048, size // 2048)
+    ts = []
+    for it in range(5):
         t0 = time.perf_counter()
-        rc = lib.hlsd_selftest_copy_host(pa, po, shape[0], shape[1], units)
-        dt = time.perf_counter() - t0
-        print(shape, units, rc, f"{dt*1e3:.1f} ms  h2d {shape[0]*units/dt/1e9:.1f} GB/s d2h {shape[1]*units/dt/1e9:.1f} GB/s", flush=True)
+        rc = lib.hlsd_selftest_copy_host(pa, po, 2048, 2048, size // 2048)
+        ts.append(time.perf_counter() - t0)
+    dt = sorted(ts)[2]
+    print(f"input {name:15s}: {dt * 1e3:7.1f} ms per GiB each way -> {size / dt / 1e9:.1f} GB/s per direction", flush=True)
+    rt.cudaFreeHost(pa)
