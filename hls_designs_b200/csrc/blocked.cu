@@ -817,8 +817,10 @@ cudaError_t chol_zero_upper_blocks(float* L, int n, long batch, cudaStream_t st)
 }
 
 cudaError_t cholesky_blocked_exact(const float* A, float* L, int n, long batch, cudaStream_t st);  // blocked_exact.cu
+cudaError_t cholesky_blocked_exact_v22(const float* A, float* L, int n, long batch, cudaStream_t st);
 
-cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int use_tensor, cudaStream_t st) {
+cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int use_tensor, int variant, cudaStream_t st) {
+    if (variant == 1) return use_tensor ? cudaErrorNotSupported : cholesky_blocked_exact_v22(A, L, n, batch, st);
     if (!use_tensor) return cholesky_blocked_exact(A, L, n, batch, st);
     if (n % NB != 0 || n < 2 * NB) return cudaErrorNotSupported;
     if ((((uintptr_t)A | (uintptr_t)L) & 15) != 0) return cudaErrorNotSupported;

@@ -43,10 +43,14 @@ struct XPanelSmem {
 // MODE 1 (LU, U12):  grid (64-column tiles right of the panel, batch); the tile is 128 panel ROWS x XR columns of
 //                    the working matrix S (= the U buffer), kept TRANSPOSED in shared memory (Xs[j][k]); unit
 //                    diagonal: no division; result back into S's buffer through `X`.
+// MODE 2 (cholesky_v2.2): grid and tile as MODE 0, S = X = the working matrix W; `L` holds the multipliers m of the
+//                    diagonal block (they play L11's part, WITHOUT a division: w_c = x_c - sum_{m<c} w_m m_cm); the
+//                    un-scaled values w go back to the working matrix and m = w / d (d = the diagonal of W) to `L`.
 // 256 threads
 template <int MODE>
 __global__ void __launch_bounds__(256, 2)
-xchol_panel_kernel(const float* __restrict__ S, float* __restrict__ X, const float* __restrict__ L, int n, int o) {
+xchol_panel_kernel(const float* __restrict__ S, float* __restrict__ X, const float* __restrict__ L, int n, int o,
+                   float* __restrict__ Mout = nullptr) {
     constexpr int LDX = XPanelSmem::LDX;
     extern __shared__ __align__(16) float xp_smem[];
     float* Xs = xp_smem;                    // [XR][LDX]
@@ -54,9 +58,9 @@ xchol_panel_kernel(const float* __restrict__ S, float* __restrict__ X, const flo
     const int tid = threadIdx.x;
     const long mat = (long)blockIdx.y * n * n;
     const int row0 = o + XB + blockIdx.x * XR;  // MODE 0: first row of this CTA; MODE 1: first column
-    const float* xsrc = MODE == 0 ? S + mat + (long)row0 * n + o : S + mat + (long)o * n + row0;
+    const float* xsrc = MODE != 1 ? S + mat + (long)row0 * n + o : S + mat + (long)o * n + row0;
     const float* lsrc = L + mat + (long)o * n + o;     // L11, written by the diagonal-block / panel kernel
-    if constexpr (MODE == 0) {
+    if constexpr (MODE != 1) {
         for (int e = tid; e < XR * (XB / 4); e += 256) {
             const int r = e >> 5, c4 = e & 31;
             *reinterpret_cast<float4*>(Xs + r * LDX + 4 * c4) = *(reinterpret_cast<const float4*>(xsrc + (long)r * n) + c4);
@@ -145,11 +149,25 @@ xchol_panel_kernel(const float* __restrict__ S, float* __restrict__ X, const flo
         }
         __syncthreads();
     }
-    if constexpr (MODE == 0) {
+    if constexpr (MODE != 1) {
         float* dst = X + mat + (long)row0 * n + o;
         for (int e = tid; e < XR * (XB / 4); e += 256) {
             const int r = e >> 5, c4 = e & 31;
             *(reinterpret_cast<float4*>(dst + (long)r * n) + c4) = *reinterpret_cast<const float4*>(Xs + r * LDX + 4 * c4);
+        }
+        if constexpr (MODE == 2) {
+            // m = w / d, column by column of the panel (IEEE division; d = the stage's un-rooted pivot)
+            float* ds = Ls;  // L11 is no longer needed: its first row holds the 128 pivots
+            __syncthreads();
+            if (tid < XB) ds[tid] = S[mat + (long)(o + tid) * n + o + tid];
+            __syncthreads();
+            float* mdst = Mout + mat + (long)row0 * n + o;
+            for (int e = tid; e < XR * (XB / 4); e += 256) {
+                const int r = e >> 5, c4 = e & 31;
+                const float4 w = *reinterpret_cast<const float4*>(Xs + r * LDX + 4 * c4);
+                const float4 d = *reinterpret_cast<const float4*>(ds + 4 * c4);
+                *(reinterpret_cast<float4*>(mdst + (long)r * n) + c4) = make_float4(xdiv(w.x, d.x), xdiv(w.y, d.y), xdiv(w.z, d.z), xdiv(w.w, d.w));
+            }
         }
     } else {
         float* dst = X + mat + (long)o * n + row0;
@@ -332,6 +350,8 @@ struct XUpdSmem {
 //                      = rows of L (multipliers, final row order), B operand = rows o..o+127 of the working matrix (U12),
 //                      which are already [k][j].
 // 256 threads; thread -> 4 x 4 outputs
+// LU == 2 (cholesky_v2.2): grid and C as LU == 0 but in place in the working matrix W (Csrc = Cdst = W); A operand = rows
+//                      of W (the un-scaled column values w), B operand = rows of `L` (the multipliers m).
 template <int LU>
 __global__ void __launch_bounds__(256, 3)
 xchol_update_kernel(const float* __restrict__ Csrc, float* __restrict__ Cdst, const float* __restrict__ L, int n, int o) {
@@ -341,7 +361,7 @@ xchol_update_kernel(const float* __restrict__ Csrc, float* __restrict__ Cdst, co
     float* Bs = xu_smem + XUpdSmem::kOp;  // [XB k][LDK]: Bs[k][j] = L[rj0 + j][o + k]  (LU: U[o + k][rj0 + j])
     const int tid = threadIdx.x;
     int ti, tj;
-    if constexpr (LU) {
+    if constexpr (LU == 1) {
         const int m = (n - o - XB) / XR;
         ti = blockIdx.x / m, tj = blockIdx.x % m;
     } else {
@@ -360,23 +380,24 @@ xchol_update_kernel(const float* __restrict__ Csrc, float* __restrict__ Cdst, co
     // consecutive threads take consecutive rows, so the scattered stores are conflict-free
     for (int e = tid; e < XR * (XB / 4); e += 256) {
         const int i = e & (XR - 1), k4 = e >> 6;
-        const float4 va = *(reinterpret_cast<const float4*>(Lm + (long)(ri0 + i) * n + o) + k4);
+        const float* Am = LU == 2 ? Csrc + mat : Lm;  // cholesky_v2.2: the A operand is the working matrix itself
+        const float4 va = *(reinterpret_cast<const float4*>(Am + (long)(ri0 + i) * n + o) + k4);
         As[(4 * k4) * LDK + i] = va.x, As[(4 * k4 + 1) * LDK + i] = va.y;
         As[(4 * k4 + 2) * LDK + i] = va.z, As[(4 * k4 + 3) * LDK + i] = va.w;
-        if (!LU && ti != tj) {
+        if (LU == 2 || (!LU && ti != tj)) {
             const float4 vb = *(reinterpret_cast<const float4*>(Lm + (long)(rj0 + i) * n + o) + k4);
             Bs[(4 * k4) * LDK + i] = vb.x, Bs[(4 * k4 + 1) * LDK + i] = vb.y;
             Bs[(4 * k4 + 2) * LDK + i] = vb.z, Bs[(4 * k4 + 3) * LDK + i] = vb.w;
         }
     }
-    if constexpr (LU) {
+    if constexpr (LU == 1) {
         const float* Um = Csrc + mat + (long)o * n + rj0;  // rows o..o+127 of the working matrix, columns of this tile
         for (int e = tid; e < XB * (XR / 4); e += 256) {
             const int k = e >> 4, j4 = e & 15;
             *reinterpret_cast<float4*>(Bs + k * LDK + 4 * j4) = *(reinterpret_cast<const float4*>(Um + (long)k * n) + j4);
         }
     }
-    const float* Bt = (LU || ti != tj) ? Bs : As;
+    const float* Bt = (LU || ti != tj) ? Bs : As;  // (LU == 2: the operands differ even on the diagonal tiles)
     const int i0 = 4 * (tid >> 4), j0 = 4 * (tid & 15);
     float c[4][4];
     const float* csrc = Csrc + mat + (long)(ri0 + i0) * n + rj0 + j0;  // Csrc = A for panel 0, L afterwards
@@ -444,6 +465,129 @@ cudaError_t cholesky_blocked_exact(const float* A, float* L, int n, long batch, 
         }
     }
     return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// cholesky_v2.2 ("revised": root-free elimination, roots at the end; Cholesky/cholesky_v2.2/model4x4/chol.cpp:28-207,
+// restated in oracle/restate.c chol_revised_one) for N >= 256, blocked like the right-looking designs above.  Per element
+// (j, i), j >= i, the reference applies  w_ji -= w_jk * m_ik  for k ascending, with m_ik = w_ik / w_kk taken at stage k,
+// and finally l_jk = m_jk * sqrt(w_kk).  The working matrix W (a workspace copy of A) keeps the un-scaled values w, the L
+// buffer the multipliers m; per 128-column panel: the diagonal block (x22_diag_kernel), the rows below it
+// (xchol_panel_kernel<2>: the panel recurrence without a division, then m = w / d), the trailing update
+// (xchol_update_kernel<2>: A operand = w, B operand = m); at the end every column is scaled by its root.
+// ------------------------------------------------------------------------------------------------
+// Diagonal block: one CTA per matrix, the 128 x 128 block in shared memory - w in the lower triangle (with the diagonal),
+// the multipliers of column k in row k of the upper triangle (m_ik at T[k][i]).  256 threads, two barriers per column.
+__global__ void __launch_bounds__(256)
+x22_diag_kernel(float* __restrict__ W, float* __restrict__ L, int n, int o) {
+    constexpr int LDT = XB + 1;
+    extern __shared__ __align__(16) float x22_tile[];  // [XB][LDT]
+    float* T = x22_tile;
+    const int tid = threadIdx.x;
+    float* wblk = W + (long)blockIdx.x * n * n + (long)o * n + o;
+    float* lblk = L + (long)blockIdx.x * n * n + (long)o * n + o;
+    for (int e = tid; e < XB * XB; e += 256) {
+        const int r = e >> 7, c = e & (XB - 1);
+        T[r * LDT + c] = wblk[(long)r * n + c];
+    }
+    __syncthreads();
+    for (int k = 0; k < XB - 1; k++) {
+        const float d = T[k * LDT + k];
+        for (int i = k + 1 + tid; i < XB; i += 256) T[k * LDT + i] = xdiv(T[i * LDT + k], d);  // m_ik
+        __syncthreads();
+        const int rows = XB - 1 - k;
+        for (int e = tid; e < rows * rows; e += 256) {
+            const int j = k + 1 + e / rows, i = k + 1 + e % rows;
+            if (i <= j) T[j * LDT + i] = xmsub(T[j * LDT + i], T[j * LDT + k], T[k * LDT + i]);
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < XB * XB; e += 256) {
+        const int r = e >> 7, c = e & (XB - 1);
+        if (c <= r) wblk[(long)r * n + c] = T[r * LDT + c];
+        lblk[(long)r * n + c] = c < r ? T[c * LDT + r] : 0.0f;  // m below the diagonal; the diagonal follows with the roots
+    }
+}
+
+// L[j][k] = m_jk * sqrt(w_kk) below the diagonal, sqrt(w_kk) on it.  grid: (n / 128 column blocks, batch), 256 threads
+__global__ void __launch_bounds__(256)
+x22_finish_kernel(const float* __restrict__ W, float* __restrict__ L, int n) {
+    __shared__ float root[XB];
+    const int c0 = blockIdx.x * XB, tid = threadIdx.x;
+    const float* w = W + (long)blockIdx.y * n * n;
+    float* l = L + (long)blockIdx.y * n * n;
+    if (tid < XB) root[tid] = xsqrt(w[(long)(c0 + tid) * n + c0 + tid]);
+    __syncthreads();
+    for (long e = tid; e < (long)(n - c0) * (XB / 4); e += 256) {
+        const int r = c0 + (int)(e >> 5), c4 = (int)(e & 31);
+        float4* p = reinterpret_cast<float4*>(l + (long)r * n + c0) + c4;
+        float4 v = *p;
+        float out[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int c = c0 + 4 * c4 + q;
+            out[q] = c < r ? xmul(out[q], root[4 * c4 + q]) : (c == r ? root[4 * c4 + q] : 0.0f);
+        }
+        *p = make_float4(out[0], out[1], out[2], out[3]);
+    }
+}
+
+cudaError_t cholesky_blocked_exact_v22(const float* A, float* L, int n, long batch, cudaStream_t st) {
+    if (n % XB != 0 || n < 2 * XB) return cudaErrorNotSupported;
+    if ((((uintptr_t)A | (uintptr_t)L) & 15) != 0) return cudaErrorNotSupported;
+    if (batch == 0) return cudaSuccess;
+    cudaError_t e;
+    if ((e = ensure_dynamic_smem(xchol_panel_kernel<2>, XPanelSmem::kBytes)) != cudaSuccess) return e;
+    if ((e = ensure_dynamic_smem(xchol_update_kernel<2>, XUpdSmem::kBytes)) != cudaSuccess) return e;
+    const size_t diag_smem = (size_t)XB * (XB + 1) * sizeof(float);
+    if ((e = ensure_dynamic_smem(x22_diag_kernel, diag_smem)) != cudaSuccess) return e;
+    const long nn = (long)n * n;
+    const int panels = n / XB;
+    // the working matrix is a workspace copy of A; large batches go in slices that bound it to 16 GB
+    const long slice = std::max<long>(1, std::min<long>(std::min<long>(batch, 32768), (long)(((size_t)16 << 30) / (sizeof(float) * nn))));
+    float* W = nullptr;
+    if ((e = ws_alloc(reinterpret_cast<void**>(&W), sizeof(float) * (size_t)slice * nn, st)) != cudaSuccess) return e;
+    for (long b0 = 0; b0 < batch && e == cudaSuccess; b0 += slice) {
+        const long cnt = std::min(slice, batch - b0);
+        const unsigned nb = (unsigned)cnt;
+        float* Ls = L + b0 * nn;
+        {
+            ProfScope ps(HLSD_PROF_OTHER, st);
+            e = cudaMemcpyAsync(W, A + b0 * nn, sizeof(float) * (size_t)cnt * nn, cudaMemcpyDeviceToDevice, st);
+        }
+        if (e != cudaSuccess) break;
+        if ((e = chol_zero_upper_blocks(Ls, n, cnt, st)) != cudaSuccess) break;
+        for (int q = 0; q < panels; q++) {
+            const int o = q * XB;
+            {
+                ProfScope ps(HLSD_PROF_DIAG, st);
+                x22_diag_kernel<<<nb, 256, diag_smem, st>>>(W, Ls, n, o);
+                count_launch();
+            }
+            const int below = n - o - XB;
+            if (below > 0) {
+                {
+                    ProfScope ps(HLSD_PROF_PANEL, st);
+                    xchol_panel_kernel<2><<<dim3(below / XR, nb), 256, XPanelSmem::kBytes, st>>>(W, W, Ls, n, o, Ls);
+                    count_launch();
+                }
+                {
+                    ProfScope ps(HLSD_PROF_UPDATE, st);
+                    const int m = below / XR;
+                    xchol_update_kernel<2><<<dim3(m * (m + 1) / 2, nb), 256, XUpdSmem::kBytes, st>>>(W, W, Ls, n, o);
+                    count_launch();
+                }
+            }
+        }
+        {
+            ProfScope ps(HLSD_PROF_OTHER, st);
+            x22_finish_kernel<<<dim3(panels, nb), 256, 0, st>>>(W, Ls, n);
+            count_launch();
+        }
+        e = cudaGetLastError();
+    }
+    ws_free(W, st);
+    return e;
 }
 
 // the two exact kernels of the blocked LU (called from lu_blocked_exact, blocked.cu): U12 and the trailing update of

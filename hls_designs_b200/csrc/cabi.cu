@@ -167,15 +167,16 @@ static int chol_dev(const float* A, float* L, int n, int64_t batch, int design, 
     if (int rc = check_flags(flags, &path, &exact, &fused)) return rc;
     // large right-looking problems go to the blocked tensor-core path unless a path was forced or the caller
     // asked for the csim's bits (HLSD_FLAG_EXACT)
-    if (path == HLSD_PATH_AUTO && variant == 0 && n >= 256 && n % 128 == 0 && (((uintptr_t)A | (uintptr_t)L) & 15) == 0)
-        path = exact ? HLSD_PATH_BLOCKED : HLSD_PATH_TENSOR;  // both blocked; BLOCKED keeps the csim's bits
+    if (path == HLSD_PATH_AUTO && n >= 256 && n % 128 == 0 && (((uintptr_t)A | (uintptr_t)L) & 15) == 0)
+        path = (exact || variant != 0) ? HLSD_PATH_BLOCKED : HLSD_PATH_TENSOR;  // both blocked; BLOCKED keeps the csim's bits
     if (path == HLSD_PATH_BLOCKED || path == HLSD_PATH_TENSOR) {
-        if (variant != 0) return fail(HLSD_ERR_UNSUPPORTED, "blocked Cholesky implements the right-looking designs only");
+        if (variant != 0 && path == HLSD_PATH_TENSOR)
+            return fail(HLSD_ERR_UNSUPPORTED, "the tensor-core Cholesky implements the right-looking designs only (cholesky_v2.2: HLSD_PATH_BLOCKED)");
         cudaError_t e = cudaSuccess;
         const int64_t kSlice = 32768;  // the blocked kernels index the batch with gridDim.y
         for (int64_t b0 = 0; b0 < batch && e == cudaSuccess; b0 += kSlice) {
             const int64_t cnt = batch - b0 < kSlice ? batch - b0 : kSlice;
-            e = cholesky_blocked(A + b0 * n * n, L + b0 * n * n, n, (long)cnt, path == HLSD_PATH_TENSOR, st);
+            e = cholesky_blocked(A + b0 * n * n, L + b0 * n * n, n, (long)cnt, path == HLSD_PATH_TENSOR, variant, st);
         }
         if (e == cudaErrorNotSupported) return fail(HLSD_ERR_UNSUPPORTED, "the blocked Cholesky paths need n % 128 == 0, n >= 256 and 16-byte aligned buffers");
         if (e != cudaSuccess) return cuda_fail(e, "cholesky_blocked");

@@ -44,8 +44,9 @@ cudaError_t qr_exact(const float* A, float* Q, float* R, int rows, int cols, lon
 
 // Blocked right-looking Cholesky for large N (n % 64 == 0, n >= 128): SIMT panel factorisation +
 // trailing update on CUDA cores in the reference's per-element order (use_tensor == 0, exact) or
-// on the tcgen05 tensor cores (use_tensor == 1).  cudaErrorNotSupported when the size is not served.
-cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int use_tensor, cudaStream_t st);
+// on the tcgen05 tensor cores (use_tensor == 1).  variant 1 (cholesky_v2.2): exact form only.
+// cudaErrorNotSupported when the size is not served.
+cudaError_t cholesky_blocked(const float* A, float* L, int n, long batch, int use_tensor, int variant, cudaStream_t st);
 
 // Bit-identical Cholesky (right-looking designs) of the m x m (m = 64, 128) diagonal block at (o, o) of matrices with row
 // stride n, held in shared memory and blocked by 32 columns (blocked_exact.cu); n == m, o == 0: a batch of m x m matrices.

@@ -69,8 +69,8 @@ typedef enum {
 #define HLSD_PATH_GROUP 2   /* warp/CTA per matrix, shared-memory resident; exact                     */
 #define HLSD_PATH_GLOBAL 3  /* one CTA per matrix in global memory: any N, exact, slow                */
 #define HLSD_PATH_BLOCKED 4 /* blocked right-looking factorisation with an exact-order SIMT trailing update:
-                               bit-identical to the csim like GLOBAL, 10-50x faster.  Cholesky: right-looking
-                               designs, n >= 256, n % 128 == 0; LU: every design incl. HLSD_LU_NOPIVOT,
+                               bit-identical to the csim like GLOBAL, 10-50x faster.  Cholesky: every design
+                               (cholesky_v2.2 in its own arithmetic), n >= 256, n % 128 == 0; LU: every design incl. HLSD_LU_NOPIVOT,
                                256 <= n <= 1024, n % 128 == 0; 16-byte aligned buffers                        */
 #define HLSD_PATH_TENSOR 5  /* blocked, tcgen05 tensor-core trailing update (3xTF32, fp32 accumulate):
                                Cholesky n >= 256, n % 128 == 0; LU 256 <= n <= 1024, n % 128 == 0;
@@ -79,7 +79,8 @@ typedef enum {
                                unless two candidates tie to round-off), residuals < 2e-6 / 5e-5      */
 #define HLSD_PATH_MASK 0xff
 /* HLSD_PATH_AUTO picks the fastest kernel that serves the request: the register/shared-memory exact
- * kernels for n <= ~230, and for the right-looking Cholesky designs / the LU designs at the
+ * kernels for n <= ~230; cholesky_v2.2 at n >= 256, n % 128 == 0 its blocked exact path; and for the right-looking
+ * Cholesky designs / the LU designs at the
  * sizes and alignment listed under HLSD_PATH_TENSOR the tensor path (so AUTO at n = 256, 512, 1024 is
  * tolerance-exact, and an unaligned pointer or n = 255 stays bit-exact).  Callers that need the csim's
  * bits at every size set HLSD_FLAG_EXACT (AUTO then picks HLSD_PATH_BLOCKED where it applies, the register /

@@ -173,9 +173,23 @@ def test_blocked_exact_cholesky_vs_oracle(n, batch):
     assert bits_equal(hd.cholesky(A, path="global")[:batch - 1], got[:batch - 1])
     assert chol_residual(A[:batch - 1], got[:batch - 1]).max() < 2e-6
     with pytest.raises(hd.HlsdError):
-        hd.cholesky(A, design="cholesky_v2.2", path="blocked")
-    with pytest.raises(hd.HlsdError):
         hd.cholesky(gen_spd(200), path="blocked")
+
+
+@pytest.mark.parametrize("n,batch", ((256, 5), (384, 3), (512, 2), (1024, 1)))
+def test_blocked_exact_cholesky_v22_vs_oracle(n, batch):
+    """cholesky_v2.2 (root-free elimination, roots at the end) at n >= 256: the blocked exact path keeps the un-scaled
+    values and the multipliers apart and applies every update in ascending k: bit-identical to the oracle and to the
+    one-CTA-per-matrix kernel; auto dispatch takes it; the tensor path refuses the design."""
+    A = gen_spd(n, batch=batch, seed=7100 + n)
+    want = restate.cholesky(A, "cholesky_v2.2", threads=8)
+    got = hd.cholesky(A, design="cholesky_v2.2", path="blocked")
+    assert bits_equal(got, want), f"n={n}: {first_mismatch(got, want)}"
+    assert bits_equal(hd.cholesky(A, design="cholesky_v2.2"), want)
+    assert bits_equal(hd.cholesky(A[:1], design="cholesky_v2.2", path="global"), want[:1])
+    assert np.abs(np.triu(got, 1)).max() == 0.0
+    with pytest.raises(hd.HlsdError):
+        hd.cholesky(A, design="cholesky_v2.2", path="tensor")
 
 
 @pytest.mark.parametrize("n,batch", ((256, 7), (384, 4), (512, 3), (1024, 2)))

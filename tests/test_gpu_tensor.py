@@ -41,7 +41,7 @@ def test_auto_dispatch_uses_tensor_path_for_large_n():
         assert np.array_equal(g, w, equal_nan=True) if g.dtype == np.float32 else np.array_equal(g, w)
     with pytest.raises(hd.HlsdError):
         hd.cholesky(A, path="tensor", exact=True)
-    # cholesky_v2.2 has no blocked form: auto falls back to the exact kernel
+    # cholesky_v2.2 has no tensor form: auto takes its blocked exact path (bit-identical)
     v22 = hd.cholesky(A[:1], design="cholesky_v2.2")
     assert np.array_equal(v22.view(np.uint32), restate.cholesky(A[:1], "cholesky_v2.2").view(np.uint32))
     with pytest.raises(hd.HlsdError):
