@@ -495,10 +495,10 @@ x22_diag_kernel(float* __restrict__ W, float* __restrict__ L, int n, int o) {
         const float d = T[k * LDT + k];
         for (int i = k + 1 + tid; i < XB; i += 256) T[k * LDT + i] = xdiv(T[i * LDT + k], d);  // m_ik
         __syncthreads();
-        const int rows = XB - 1 - k;
-        for (int e = tid; e < rows * rows; e += 256) {
-            const int j = k + 1 + e / rows, i = k + 1 + e % rows;
-            if (i <= j) T[j * LDT + i] = xmsub(T[j * LDT + i], T[j * LDT + k], T[k * LDT + i]);
+        // rows j = k+1 .. 127, eight threads per row striding over the columns i = k+1 .. j of the lower triangle
+        for (int j = k + 1 + (tid >> 3); j < XB; j += 32) {
+            const float wjk = T[j * LDT + k];
+            for (int i = k + 1 + (tid & 7); i <= j; i += 8) T[j * LDT + i] = xmsub(T[j * LDT + i], wjk, T[k * LDT + i]);
         }
         __syncthreads();
     }
