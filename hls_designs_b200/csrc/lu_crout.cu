@@ -14,7 +14,8 @@
 //       K2 lu_cpanel_kernel       (SIMT)     pivoted elimination of the panel, thread = row, positions tracked in
 //                                            registers, ONE barrier per column; writes M2, U11, P, the new posmap
 //       K3 blk_diag2_kernel<true> (SIMT)     W = inv(L11), L11 gathered from M2 through posmap
-//       K4 lu_ll_kernel<LL_ROW>   (tcgen05)  X12^T[c][m] = A[piv_m][c] - sum_{k<o} UT[c][k] M2[piv_m][k]  (the 128 pivot rows)
+//       K4 lu_ll_kernel<LL_ROW>   (tcgen05)  X12[m][c] = A[piv_m][c] - sum_{k<o} M2[piv_m][k] UT[c][k]  (the 128 pivot rows), stored
+//                                            transposed (T0[c][m])
 //          lu_trsm_kernel         (tcgen05)  U12^T = X12^T W^T  -> UT[c][o..o+127] and U[o..o+127][c]
 //     so C is read once (from A) and written once per element, and the K loops are 128 p long (as in the Cholesky
 //     path's blk_ll2_kernel) instead of a rank-128 update per panel with a read-modify-write of the trailing matrix.
@@ -67,16 +68,19 @@ lu_panel0_load_kernel(const float* __restrict__ A, float* __restrict__ PWT, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Long-K tensor-core kernel of the Crout scheme: D = Aop * Bop^T over K = o (all finished panels at once), result =
-// (tile of A, through posmap) - D.  The pipeline is blk_ll2_kernel's (blocked.cu): 512 threads load fp32 operand chunks
-// two chunks ahead into registers, write each chunk to shared memory as the raw (= tf32 hi) and the lo tile in the
-// canonical K-major SWIZZLE_128B layout, one thread issues the 3xTF32 MMAs into TMEM; two output tiles per CTA share
-// the B operand.
-//   LL_COL (K1): output rows = positions o + 128 (2 bx + h) + r; Aop rows = M2[pm[position]], Bop rows = UT[o + c];
-//                thread = accumulator row = position; result goes to PWT[c][position - o] (coalesced over positions).
-//   LL_ROW (K4): output rows = columns c = o + 128 + 128 (2 bx + h) + r of U12^T; Aop rows = UT[c], Bop rows =
-//                M2[pm[o + m]] (the panel's pivot rows, pm = posmap AFTER the panel); thread = accumulator row = column
-//                c; the tile of A is read transposed (coalesced over c) and the result goes to T0[c - o - 128][m].
+// Long-K tensor-core kernel of the Crout scheme: a product over K = o (all finished panels at once), result =
+// (tile of A, through posmap) - product.  The pipeline is blk_ll2_kernel's (blocked.cu): 512 threads load fp32 operand
+// chunks three chunks ahead into registers, write each chunk to shared memory as the raw (= tf32 hi) and the lo tile in
+// the canonical K-major SWIZZLE_128B layout, one thread issues the 3xTF32 MMAs into TMEM.  A CTA produces two paired
+// tiles that share one operand: the SHARED tile (128 rows) is the M operand, the two paired tiles - contiguous in shared
+// memory - form one 256-row N operand, so the accumulator is 128 lanes (rows of the shared tile) x 256 columns (rows of
+// the paired tiles), i.e. the result comes out transposed and the epilogue thread = a row of the shared tile.
+//   LL_COL (K1): paired tiles = positions o + 128 (2 bx + h) + r, rows M2[pm[position]]; shared tile = the panel's
+//                columns c, rows UT[o + c].  Thread = column c: the tile of A is read coalesced over c, the result goes to
+//                PWT[c][position - o], 32 consecutive positions per thread.
+//   LL_ROW (K4): paired tiles = columns c = o + 128 + 128 (2 bx + h) + r of U12, rows UT[c]; shared tile = the panel's
+//                128 pivot rows, rows M2[pm[o + m]] (pm = posmap AFTER the panel).  Thread = pivot row m: the tile of A is
+//                read from the thread's own row, the result X12^T goes to T0[c - o - 128][m], coalesced over m.
 // grid: (ceil(tiles / 2), batch)
 // ------------------------------------------------------------------------------------------------
 struct LlSmem {
