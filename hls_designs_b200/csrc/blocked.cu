@@ -596,8 +596,10 @@ blk_mma_kernel(const float* __restrict__ S, float* __restrict__ L, const float* 
 // (A cp.async ring would cost a third pass over shared memory - write raw, read raw, write lo.)
 // Two row blocks per CTA: tiles (r0, q) and (r0 + 1, q) share the B operand (block row q), which cuts
 // the panel bytes each step re-reads from L2/HBM by a quarter - the measured bound of the update:
-// three operand tiles per chunk (A0, A1, B: raw + lo, double buffered = 192 KB) and two accumulators
-// in TMEM (256 columns).  grid: (ceil((panels - q) / 2), batch)
+// three operand tiles per chunk (A0, A1, B: raw + lo, double buffered = 192 KB).  The shared tile is the M operand and
+// the two row tiles - contiguous in shared memory - one 256-row N operand, so ONE 128 x 256 accumulator holds the two
+// results TRANSPOSED (lane = column of block column q): the epilogue reads C from A and writes X to L straight from
+// registers, coalesced over the columns, without a shared-memory stage.  grid: (ceil((panels - q) / 2), batch)
 // ------------------------------------------------------------------------------------------------
 struct Ll2Smem {
     static constexpr int kTile = 128 * 32 * 4;
