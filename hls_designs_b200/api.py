@@ -148,7 +148,7 @@ def qr(A, design="qr_v2.1", path="auto", exact=False, fused=False, devices=None)
     return Q, R
 
 
-OPTIONS = {"chol_slab": 1, "lu32_kernel": 2, "diag_kernel": 3, "lockstep": 4, "qr_threads": 5, "chol_tile": 6}
+OPTIONS = {"chol_slab": 1, "diag_kernel": 3, "lockstep": 4, "qr_threads": 5, "chol_tile": 6}
 
 
 def set_option(name, value):

@@ -6,8 +6,8 @@
 //
 // Kernels:
 //   lu_tpm_kernel<N>      thread-per-matrix in registers, N = 4: staged slabs.
-//   lu_regs_kernel<N,R>   R lanes per matrix, all in registers, N in {8, 16, 32}: pivot row by shuffle.
-//   lu_lane_kernel<N>     one lane per row, N = 64 (two warps per matrix) and N = 128 (four).
+//   lu_regs_kernel<N,R>   R lanes per matrix, all in registers, N in {8, 16}: pivot row by shuffle.
+//   lu_lane_kernel<N>     one lane per row, N = 32 (one warp per matrix), 64 (two) and 128 (four).
 //   lu_group_kernel<G>    G threads per matrix, matrix resident in shared memory.
 //   lu_global_kernel      one CTA per matrix, in place in global memory (any N; exact; slow).
 #include "common.cuh"
@@ -714,8 +714,8 @@ static cudaError_t lu_dispatch(const float* A, float* L, float* U, int* P, int n
         // (eight lanes per matrix at N = 16: 0.88 G fact/s with 24 warps, 0.81 G with 16, against 1.03 G for four lanes)
         if (aligned && n == 16) return launch_lu_regs<16, 4, 12, FUSED, true>(A, L, U, P, batch, pivoting, st);  // U rows straight out: +10 %
         if (aligned && n == 32) {
-            // measured (round 2, batch 259441): lane-per-row kernel 148 M fact/s, rows-in-registers kernel 116 M
-            if (option(HLSD_OPT_LU32_KERNEL) == 1) return launch_lu_regs<32, 16, 10, FUSED>(A, L, U, P, batch, pivoting, st);
+            // measured (round 2, batch 259441): lane-per-row kernel 227 M fact/s; the rows-in-registers kernel
+            // (lu_regs_kernel<32, 16>) managed 116 M (76 M after the lane kernel's last changes) and is no longer built
             return launch_lu_lane<32, FUSED>(A, L, U, P, batch, pivoting, st);
         }
         if (aligned && n == 64) return launch_lu_lane<64, FUSED>(A, L, U, P, batch, pivoting, st);

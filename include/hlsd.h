@@ -142,7 +142,7 @@ const char* hlsd_version(void);
  * returns HLSD_ERR_INVALID for an unknown option. */
 #define HLSD_OPT_CHOL_SLAB 1    /* Cholesky register kernels: 0 = default (N = 32 dense slab, N = 64 packed lower-triangle
                                    slab), 1 = the other layout, 2 = N = 32 packed with 8 warps per SM                */
-#define HLSD_OPT_LU32_KERNEL 2  /* LU 32x32: 0 = lane-per-row kernel (default), 1 = rows-in-registers kernel          */
+#define HLSD_OPT_RESERVED_2 2   /* (was the LU 32x32 kernel choice; the rows-in-registers kernel is no longer built)     */
 #define HLSD_OPT_DIAG_KERNEL 3  /* tensor paths, 128x128 diagonal block: 0 = default, 1 = the other implementation   */
 #define HLSD_OPT_LOCKSTEP 4     /* unrolled register kernels (Cholesky 32/64, LU 64/128, QR 16/32): 0 = default, 1 = the other
                                    of {free-running warps, one CTA-wide barrier per step}                             */

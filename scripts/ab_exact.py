@@ -27,7 +27,7 @@ CASES = {
     "chol128": ("chol", 128, [("tile", {}, False), ("regs (blk_diag)", {"chol_tile": 1}, False), ("tile+fused", {}, True)]),
     "lu8": ("lu", 8, [("default", {}, False)]),
     "lu16": ("lu", 16, [("default", {}, False), ("fused", {}, True)]),
-    "lu32": ("lu", 32, [("lane", {}, False), ("regs", {"lu32_kernel": 1}, False), ("lane+fused", {}, True)]),
+    "lu32": ("lu", 32, [("lane", {}, False), ("lane+fused", {}, True)]),
     "lu64": ("lu", 64, [("default", {}, False), ("lockstep", {"lockstep": 1}, False), ("fused", {}, True)]),
     "lu128": ("lu", 128, [("lane", {}, False), ("lockstep", {"lockstep": 1}, False), ("fused", {}, True)]),
     "qr8": ("qr", 8, [("default", {}, False)]),
